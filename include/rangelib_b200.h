@@ -1,0 +1,149 @@
+/*
+ * rangelib_b200.h -- C ABI of the B200-native batched lidar scan path.
+ *
+ * Drop-in boundary for the scan path of felrock/PyRacecarSimulator.  Every entry point
+ * replaces one interface of the external `range_libc` extension as the reference binds
+ * it (all citations relative to the reference checkout):
+ *
+ *   range_libc.PyOMap(map_msg)                 scripts/ros_interface.py:210,
+ *                                              scripts/mcts_driver.py:278
+ *       -> rl_map_from_occupancy / rl_map_from_image / rl_map_from_cells
+ *   range_libc.PyRayMarching(omap, mrx)        scripts/scan_simulator.py:72-73
+ *   range_libc.PyRayMarchingGPU(omap, mrx)     scripts/scan_simulator.py:75-76
+ *       -> rl_marcher_create          (the distance transform upstream builds on the host
+ *                                      inside these constructors is built on the GPU by
+ *                                      rl_map_from_*)
+ *   .calc_range_many(ins, outs)                scripts/two_player/scan.py:69-70
+ *       -> rl_calc_range_many[_host]
+ *   .calc_range_many(ins, outs, fov, num_rays) scripts/scan_simulator.py:103-106, :130-133
+ *       -> rl_calc_range_fan[_host]   (pose_stride_rows = num_rays is the fork's layout)
+ *   .calc_range_repeat_angles(ins, angles, outs)   upstream RangeLibc.pyx (north_star)
+ *       -> rl_calc_range_repeat_angles[_host]
+ *   racecar.PyCar.isCrashed(scans, num_rays, poses) after scanMany
+ *                                              scripts/racecar_simulator_v2.py:146-167,
+ *                                              racecar/src/racecar.cpp:305-328
+ *       -> rl_scan_crash              (fan march with the crash test as its epilogue)
+ *   MCTS.rollout (bicycle steps + checkCollisionMany)   scripts/mcts.py:202-245,
+ *                                              racecar/src/racecar.cpp:53-237
+ *       -> rl_rollout                 (fused step + scan + crash, north_star (c))
+ *
+ * Conventions
+ *   - Plain C: pointers and sizes only.  Functions return RL_OK (0) or a negative
+ *     rl_status; rl_last_error() returns a thread-local message.  Nothing here ever
+ *     exits the process or falls back to the CPU.
+ *   - `d_` pointers are DEVICE pointers on the map's device; the call is enqueued on
+ *     `stream` (a cudaStream_t passed as void*, NULL = the legacy default stream) and
+ *     returns without synchronising.  `_host` variants take HOST pointers, stage through
+ *     pinned memory owned by the marcher, and return when `outs` is filled.
+ *   - poses are (x, y, theta) fp32 triples in the map.yaml world frame (metres, radians);
+ *     ranges are fp32 metres.  max_range is in pixels (scripts/racecar_simulator_v2.py:196).
+ *   - A map is immutable once built and may be shared by any number of marchers and
+ *     threads; a marcher serialises its own `_host` calls with an internal mutex and is
+ *     otherwise stateless, so concurrent device-pointer calls on different streams are safe.
+ */
+#ifndef RANGELIB_B200_H
+#define RANGELIB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RL_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define RL_API __attribute__((visibility("default")))
+#else
+#define RL_API
+#endif
+
+typedef enum rl_status {
+    RL_OK = 0,
+    RL_ERR_BAD_ARG = -1,   /* null pointer, non-positive size, unsupported size */
+    RL_ERR_CUDA = -2,      /* a CUDA runtime call failed; see rl_last_error()   */
+    RL_ERR_NO_DEVICE = -3, /* no CUDA device / device index out of range        */
+    RL_ERR_OOM = -4        /* host or device allocation failed                  */
+} rl_status;
+
+/* marcher flags */
+#define RL_FLAG_DEFAULT 0u
+#define RL_FLAG_TRIG_TABLE 1u /* fast mode: per-beam sin/cos by angle addition from a  */
+                              /* shared-memory table (not bit-identical to cosf/sinf)   */
+
+/* dist2 value of a cell from which no occupied cell is reachable (empty map) */
+#define RL_DIST2_INF 0x3fffffff
+
+typedef struct rl_map rl_map;
+typedef struct rl_marcher rl_marcher;
+
+RL_API int32_t rl_abi_version(void);
+RL_API const char *rl_last_error(void);
+RL_API int32_t rl_device_count(int32_t *count);
+
+/* ---- map ingest (GPU: threshold -> occupancy -> exact integer squared EDT -> sqrt) ---- */
+
+/* From image pixels as stored in the PGM (rows top to bottom, `width` columns), applying  */
+/* map_server's trinary thresholds and y-flip, then (binarise != 0) the reference's        */
+/* `>0 -> 255 else 0` (scripts/ros_interface.py:80-86), then PyOMap's `> 10` cut.          */
+RL_API int32_t rl_map_from_image(const uint8_t *pixels, int32_t width, int32_t height, int32_t negate,
+                          double occupied_thresh, double free_thresh, int32_t binarise,
+                          double resolution, double origin_x, double origin_y, double origin_yaw,
+                          int32_t device, rl_map **out);
+
+/* From OccupancyGrid.data (int8, row-major from the bottom-left cell, width = columns). */
+RL_API int32_t rl_map_from_occupancy(const int8_t *data, int32_t width, int32_t height, int32_t binarise,
+                              double resolution, double origin_x, double origin_y,
+                              double origin_yaw, int32_t device, rl_map **out);
+
+/* From an already-cut boolean grid (non-zero = occupied), same cell order. */
+RL_API int32_t rl_map_from_cells(const uint8_t *occupied, int32_t width, int32_t height,
+                          double resolution, double origin_x, double origin_y, double origin_yaw,
+                          int32_t device, rl_map **out);
+
+RL_API int32_t rl_map_shape(const rl_map *map, int32_t *width, int32_t *height, int32_t *device);
+/* Host copies for bit-exact checks: occupancy (uint8 0/1), squared distance (int32,      */
+/* RL_DIST2_INF when unreachable) and distance (fp32 pixels), each width*height, row-major */
+/* from the bottom-left cell.                                                              */
+RL_API int32_t rl_map_get_occupancy(const rl_map *map, uint8_t *out);
+RL_API int32_t rl_map_get_dist2(const rl_map *map, int32_t *out);
+RL_API int32_t rl_map_get_dist(const rl_map *map, float *out);
+/* Device pointer of the fp32 distance field (borrowed; valid until rl_map_destroy). */
+RL_API int32_t rl_map_dist_device(const rl_map *map, const float **d_dist);
+/* Device time of the last ingest on this map, milliseconds (CUDA events). */
+RL_API int32_t rl_map_ingest_ms(const rl_map *map, float *ms);
+RL_API int32_t rl_map_destroy(rl_map *map);
+
+/* ---- marcher ---- */
+RL_API int32_t rl_marcher_create(const rl_map *map, float max_range_px, uint32_t flags, rl_marcher **out);
+RL_API int32_t rl_marcher_destroy(rl_marcher *m);
+
+/* one (x, y, theta) row per ray: outs[i] = range(ins[i]) */
+RL_API int32_t rl_calc_range_many(rl_marcher *m, const float *d_ins, float *d_outs, int64_t num_rays_total,
+                           void *stream);
+RL_API int32_t rl_calc_range_many_host(rl_marcher *m, const float *ins, float *outs, int64_t num_rays_total);
+
+/* pose k at row k*pose_stride_rows of d_poses; beam j heads theta - fov/2 + j*fov/num_rays; */
+/* outs[k*num_rays + j].  pose_stride_rows = 1: compact (B,3); = num_rays: the fork's layout.  */
+RL_API int32_t rl_calc_range_fan(rl_marcher *m, const float *d_poses, int64_t pose_stride_rows,
+                          float *d_outs, int64_t num_poses, int32_t num_rays, float fov,
+                          void *stream);
+RL_API int32_t rl_calc_range_fan_host(rl_marcher *m, const float *poses, int64_t pose_stride_rows,
+                               float *outs, int64_t num_poses, int32_t num_rays, float fov);
+
+/* outs[i*num_angles + a] = range(x_i, y_i, theta_i + angles[a]) */
+RL_API int32_t rl_calc_range_repeat_angles(rl_marcher *m, const float *d_poses, const float *d_angles,
+                                    float *d_outs, int64_t num_poses, int32_t num_angles,
+                                    void *stream);
+RL_API int32_t rl_calc_range_repeat_angles_host(rl_marcher *m, const float *poses, const float *angles,
+                                         float *outs, int64_t num_poses, int32_t num_angles);
+
+/* Number of distance-field loads ("march steps") the last *_host call performed, when the */
+/* marcher was asked to count them (rl_marcher_count_steps(m, 1)); used by the roofline.    */
+RL_API int32_t rl_marcher_count_steps(rl_marcher *m, int32_t enable);
+RL_API int32_t rl_marcher_last_steps(rl_marcher *m, uint64_t *steps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RANGELIB_B200_H */

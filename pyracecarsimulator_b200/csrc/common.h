@@ -1,0 +1,68 @@
+// common.h -- internal types shared by the translation units behind include/rangelib_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+
+#include "../../include/rangelib_b200.h"
+
+namespace rl {
+
+void set_error(const std::string &msg);
+int32_t fail(int32_t code, const std::string &msg);
+
+#define RL_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return rl::fail(_e == cudaErrorMemoryAllocation ? RL_ERR_OOM : RL_ERR_CUDA,        \
+                            std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+    } while (0)
+
+// Switches to `device` for the lifetime of the object and restores the caller's device.
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != device && cudaSetDevice(device) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+// World <-> grid constants of an OMap, all narrowed to fp32 exactly as
+// PyOMap / RangeMethod::numpy_calc_range do on the host.
+struct WorldFrame {
+    float scale, angle, origin_x, origin_y, sin_angle, cos_angle, inv_scale, rotation_const;
+};
+
+// Passed by value to every march kernel.
+struct MarchParams {
+    const float *dist;  // dist[row * cols + col], fp32 pixels
+    int rows, cols;     // rows = OMap.width (msg.info.height), cols = OMap.height (msg.info.width)
+    float frows, fcols;
+    float max_range;    // pixels
+    WorldFrame w;
+};
+
+}  // namespace rl
+
+struct rl_map {
+    int device = 0;
+    int rows = 0, cols = 0;
+    rl::WorldFrame world{};
+    uint8_t *d_occ = nullptr;   // rows*cols, 0/1
+    int32_t *d_dist2 = nullptr; // rows*cols exact squared distance
+    float *d_dist = nullptr;    // rows*cols sqrt
+    float ingest_ms = 0.f;
+    std::atomic<int> refs{1};
+};
+
+void rl_map_retain(const rl_map *m);
+void rl_map_release(const rl_map *m);

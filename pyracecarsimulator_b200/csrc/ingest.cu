@@ -1,0 +1,318 @@
+// ingest.cu -- map ingest on the GPU: source cells -> occupancy -> exact integer squared
+// Euclidean distance transform -> fp32 distance field.  Replaces the host-side work of
+// range_libc's PyOMap + DistanceTransform constructors (reference call sites
+// scripts/ros_interface.py:80-86, :210 and scripts/scan_simulator.py:72-76).
+//
+// Kernel pair (north_star (a)):
+//   edt_cols_kernel  one thread per map column: classifies every source cell through a
+//                    256-entry bit LUT (map_server thresholds / binarisation / `> 10` cut are
+//                    all pure functions of one byte, so the host folds them into the LUT with
+//                    the reference's double arithmetic), applies map_server's y-flip, writes
+//                    the occupancy byte and the distance g to the nearest occupied cell in
+//                    the same column (down sweep then up sweep), as saturating u16.
+//   edt_rows_kernel  one CTA per map row with the row's g^2 staged in shared memory: each
+//                    thread takes the lower envelope min_k (k^2 + g^2[q +- k]) by an outward
+//                    scan that stops as soon as k^2 >= best, which is exact in integers and
+//                    costs O(distance) per cell; writes d^2 (int32) and sqrt_rn((float)d^2).
+// For max(rows, cols) <= 2896 the reference's float Felzenszwalb transform returns exactly
+// this integer d^2, so the fp32 field is bit-identical to the reference's.
+#include <cmath>
+#include <new>
+
+#include "common.h"
+
+namespace {
+
+constexpr uint32_t G_INF = 0xFFFFu;         // u16 column distance: no occupied cell in the column
+constexpr uint32_t G2_INF = 0xFFFFFFFFu;
+constexpr int MAX_SIDE = 16384;             // keeps every real d^2 below RL_DIST2_INF
+
+struct ByteLut { uint32_t w[8]; };          // bit p set <=> source byte p is an occupied cell
+
+__device__ __forceinline__ uint32_t lut_bit(const ByteLut &lut, uint32_t p)
+{
+    return (lut.w[p >> 5] >> (p & 31u)) & 1u;
+}
+
+constexpr int COLS_BATCH = 8;
+
+__global__ void __launch_bounds__(32)
+edt_cols_kernel(const uint8_t *__restrict__ src, int rows, int cols, int flip, ByteLut lut,
+                uint8_t *__restrict__ occ, uint16_t *__restrict__ g)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    uint32_t run = G_INF;
+    // down sweep, loads batched COLS_BATCH deep so they overlap (they do not depend on `run`)
+    for (int r0 = 0; r0 < rows; r0 += COLS_BATCH) {
+        uint32_t p[COLS_BATCH];
+#pragma unroll
+        for (int i = 0; i < COLS_BATCH; ++i) {
+            int r = r0 + i;
+            int sr = flip ? rows - 1 - r : r;
+            p[i] = (r < rows) ? src[(size_t)sr * cols + c] : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < COLS_BATCH; ++i) {
+            int r = r0 + i;
+            if (r < rows) {
+                uint32_t o = lut_bit(lut, p[i]);
+                run = o ? 0u : min(run + 1u, G_INF);
+                occ[(size_t)r * cols + c] = (uint8_t)o;
+                g[(size_t)r * cols + c] = (uint16_t)run;
+            }
+        }
+    }
+    // up sweep
+    run = G_INF;
+    for (int r0 = rows - 1; r0 >= 0; r0 -= COLS_BATCH) {
+        uint32_t gv[COLS_BATCH];
+#pragma unroll
+        for (int i = 0; i < COLS_BATCH; ++i) {
+            int r = r0 - i;
+            gv[i] = (r >= 0) ? g[(size_t)r * cols + c] : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < COLS_BATCH; ++i) {
+            int r = r0 - i;
+            if (r >= 0) {
+                run = (gv[i] == 0u) ? 0u : min(run + 1u, G_INF);
+                if (run < gv[i]) g[(size_t)r * cols + c] = (uint16_t)run;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+edt_rows_kernel(const uint16_t *__restrict__ g, int rows, int cols,
+                int32_t *__restrict__ dist2, float *__restrict__ dist)
+{
+    extern __shared__ uint32_t g2[];  // cols entries
+    const int r = blockIdx.x;
+    const uint16_t *grow = g + (size_t)r * cols;
+    for (int q = threadIdx.x; q < cols; q += blockDim.x) {
+        uint32_t v = grow[q];
+        g2[q] = (v >= G_INF) ? G2_INF : v * v;
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < cols; q += blockDim.x) {
+        uint32_t best = g2[q];
+        const int reach = max(q, cols - 1 - q);
+        for (int k = 1; k <= reach; ++k) {
+            const uint32_t kk = (uint32_t)k * (uint32_t)k;
+            if (kk >= best) break;
+            const int l = q - k, rr = q + k;
+            if (l >= 0) {
+                uint32_t v = g2[l];
+                if (v != G2_INF) best = min(best, kk + v);
+            }
+            if (rr < cols) {
+                uint32_t v = g2[rr];
+                if (v != G2_INF) best = min(best, kk + v);
+            }
+        }
+        const size_t o = (size_t)r * cols + q;
+        if (best == G2_INF) {
+            dist2[o] = RL_DIST2_INF;
+            dist[o] = sqrtf(1e20f);  // what the reference's INF = 1e20 transform leaves on an empty map
+        } else {
+            dist2[o] = (int32_t)best;
+            dist[o] = sqrtf((float)best);
+        }
+    }
+}
+
+rl::WorldFrame make_world(double resolution, double ox, double oy, double yaw)
+{
+    rl::WorldFrame w;
+    const double angle = -1.0 * yaw;  // PyOMap: world_angle = -yaw(origin quaternion)
+    w.scale = (float)resolution;
+    w.angle = (float)angle;
+    w.origin_x = (float)ox;
+    w.origin_y = (float)oy;
+    w.sin_angle = (float)std::sin(angle);
+    w.cos_angle = (float)std::cos(angle);
+    w.inv_scale = (float)(1.0 / (double)w.scale);
+    w.rotation_const = (float)(-1.0 * (double)w.angle - 3.0 * M_PI / 2.0);
+    return w;
+}
+
+int32_t build_map(const uint8_t *src, int width, int height, int flip, const ByteLut &lut,
+                  double resolution, double ox, double oy, double yaw, int device, rl_map **out)
+{
+    if (!src || !out) return rl::fail(RL_ERR_BAD_ARG, "map ingest: null pointer");
+    if (width <= 0 || height <= 0 || width > MAX_SIDE || height > MAX_SIDE)
+        return rl::fail(RL_ERR_BAD_ARG, "map ingest: width/height must be in [1, 16384]");
+    if (!(resolution > 0.0)) return rl::fail(RL_ERR_BAD_ARG, "map ingest: resolution must be > 0");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return rl::fail(RL_ERR_NO_DEVICE, "map ingest: no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return rl::fail(RL_ERR_NO_DEVICE, "map ingest: bad device index");
+    rl::DeviceGuard guard(device);
+    if (!guard.ok) return rl::fail(RL_ERR_CUDA, "map ingest: cudaSetDevice failed");
+
+    rl_map *m = new (std::nothrow) rl_map();
+    if (!m) return rl::fail(RL_ERR_OOM, "map ingest: host allocation failed");
+    m->device = device;
+    m->rows = height;  // msg.info.height
+    m->cols = width;   // msg.info.width
+    m->world = make_world(resolution, ox, oy, yaw);
+    const size_t n = (size_t)width * height;
+    uint8_t *d_src = nullptr;
+    uint16_t *d_g = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    auto cleanup = [&](bool all) {
+        cudaFree(d_src);
+        cudaFree(d_g);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (all) { cudaFree(m->d_occ); cudaFree(m->d_dist2); cudaFree(m->d_dist); delete m; }
+    };
+#define RL_TRY(expr)                                                                           \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            cleanup(true);                                                                     \
+            return rl::fail(_e == cudaErrorMemoryAllocation ? RL_ERR_OOM : RL_ERR_CUDA,        \
+                            std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+        }                                                                                      \
+    } while (0)
+    RL_TRY(cudaMalloc(&d_src, n));
+    RL_TRY(cudaMalloc(&d_g, n * sizeof(uint16_t)));
+    RL_TRY(cudaMalloc(&m->d_occ, n));
+    RL_TRY(cudaMalloc(&m->d_dist2, n * sizeof(int32_t)));
+    RL_TRY(cudaMalloc(&m->d_dist, n * sizeof(float)));
+    RL_TRY(cudaMemcpy(d_src, src, n, cudaMemcpyHostToDevice));
+    RL_TRY(cudaEventCreate(&e0));
+    RL_TRY(cudaEventCreate(&e1));
+    const size_t smem = (size_t)width * sizeof(uint32_t);
+    RL_TRY(cudaFuncSetAttribute(edt_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RL_TRY(cudaEventRecord(e0, 0));
+    edt_cols_kernel<<<(width + 31) / 32, 32>>>(d_src, height, width, flip, lut, m->d_occ, d_g);
+    edt_rows_kernel<<<height, 256, smem>>>(d_g, height, width, m->d_dist2, m->d_dist);
+    RL_TRY(cudaGetLastError());
+    RL_TRY(cudaEventRecord(e1, 0));
+    RL_TRY(cudaEventSynchronize(e1));
+    RL_TRY(cudaEventElapsedTime(&m->ingest_ms, e0, e1));
+#undef RL_TRY
+    cleanup(false);
+    *out = m;
+    return RL_OK;
+}
+
+}  // namespace
+
+void rl_map_retain(const rl_map *m) { const_cast<rl_map *>(m)->refs.fetch_add(1); }
+
+void rl_map_release(const rl_map *cm)
+{
+    rl_map *m = const_cast<rl_map *>(cm);
+    if (m->refs.fetch_sub(1) == 1) {
+        rl::DeviceGuard guard(m->device);
+        cudaFree(m->d_occ);
+        cudaFree(m->d_dist2);
+        cudaFree(m->d_dist);
+        delete m;
+    }
+}
+
+extern "C" {
+
+int32_t rl_map_from_image(const uint8_t *pixels, int32_t width, int32_t height, int32_t negate,
+                          double occupied_thresh, double free_thresh, int32_t binarise,
+                          double resolution, double origin_x, double origin_y, double origin_yaw,
+                          int32_t device, rl_map **out)
+{
+    // map_server trinary rule per byte value, in double like map_server, then the reference's
+    // binarisation and PyOMap's cut.
+    ByteLut lut{};
+    for (int p = 0; p < 256; ++p) {
+        double shade = negate ? p / 255.0 : (255 - p) / 255.0;
+        int v = -1;
+        if (shade > occupied_thresh) v = 100;
+        else if (shade < free_thresh) v = 0;
+        if (binarise) v = (v > 0) ? 255 : 0;
+        if (v > 10) lut.w[p >> 5] |= 1u << (p & 31);
+    }
+    return build_map(pixels, width, height, /*flip=*/1, lut, resolution, origin_x, origin_y,
+                     origin_yaw, device, out);
+}
+
+int32_t rl_map_from_occupancy(const int8_t *data, int32_t width, int32_t height, int32_t binarise,
+                              double resolution, double origin_x, double origin_y,
+                              double origin_yaw, int32_t device, rl_map **out)
+{
+    ByteLut lut{};
+    for (int p = 0; p < 256; ++p) {
+        int v = (int8_t)p;
+        if (binarise) v = (v > 0) ? 255 : 0;
+        if (v > 10) lut.w[p >> 5] |= 1u << (p & 31);
+    }
+    return build_map(reinterpret_cast<const uint8_t *>(data), width, height, /*flip=*/0, lut,
+                     resolution, origin_x, origin_y, origin_yaw, device, out);
+}
+
+int32_t rl_map_from_cells(const uint8_t *occupied, int32_t width, int32_t height,
+                          double resolution, double origin_x, double origin_y, double origin_yaw,
+                          int32_t device, rl_map **out)
+{
+    ByteLut lut{};
+    for (int p = 1; p < 256; ++p) lut.w[p >> 5] |= 1u << (p & 31);
+    return build_map(occupied, width, height, /*flip=*/0, lut, resolution, origin_x, origin_y,
+                     origin_yaw, device, out);
+}
+
+int32_t rl_map_shape(const rl_map *map, int32_t *width, int32_t *height, int32_t *device)
+{
+    if (!map) return rl::fail(RL_ERR_BAD_ARG, "rl_map_shape: null map");
+    if (width) *width = map->cols;
+    if (height) *height = map->rows;
+    if (device) *device = map->device;
+    return RL_OK;
+}
+
+static int32_t copy_out(const rl_map *map, const void *d_src, void *out, size_t elem)
+{
+    if (!map || !out) return rl::fail(RL_ERR_BAD_ARG, "rl_map_get_*: null pointer");
+    rl::DeviceGuard guard(map->device);
+    RL_CUDA(cudaMemcpy(out, d_src, (size_t)map->rows * map->cols * elem, cudaMemcpyDeviceToHost));
+    return RL_OK;
+}
+
+int32_t rl_map_get_occupancy(const rl_map *map, uint8_t *out)
+{
+    return copy_out(map, map ? map->d_occ : nullptr, out, 1);
+}
+
+int32_t rl_map_get_dist2(const rl_map *map, int32_t *out)
+{
+    return copy_out(map, map ? map->d_dist2 : nullptr, out, sizeof(int32_t));
+}
+
+int32_t rl_map_get_dist(const rl_map *map, float *out)
+{
+    return copy_out(map, map ? map->d_dist : nullptr, out, sizeof(float));
+}
+
+int32_t rl_map_dist_device(const rl_map *map, const float **d_dist)
+{
+    if (!map || !d_dist) return rl::fail(RL_ERR_BAD_ARG, "rl_map_dist_device: null pointer");
+    *d_dist = map->d_dist;
+    return RL_OK;
+}
+
+int32_t rl_map_ingest_ms(const rl_map *map, float *ms)
+{
+    if (!map || !ms) return rl::fail(RL_ERR_BAD_ARG, "rl_map_ingest_ms: null pointer");
+    *ms = map->ingest_ms;
+    return RL_OK;
+}
+
+int32_t rl_map_destroy(rl_map *map)
+{
+    if (!map) return rl::fail(RL_ERR_BAD_ARG, "rl_map_destroy: null map");
+    rl_map_release(map);
+    return RL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,206 @@
+"""The march kernels (csrc/march.cu) through the range_libc-compatible shim, against the oracle
+on the same seeded inputs and against the committed golden vectors.  Bar (north_star): every
+range within max(1e-4 rel, 0.5 cell), >= 99.9 % of beams bit-identical, max_range / out-of-map
+handling identical."""
+import numpy as np
+import pytest
+
+from pyracecarsimulator_b200 import maps, range_libc
+from gpu_util import assert_ranges_match, build_synth
+
+pytestmark = pytest.mark.gpu
+
+FOV = 4.71
+
+
+@pytest.fixture(scope="module")
+def col(orc, colombia, colombia_scan):
+    grid = colombia_scan["grid"]
+    binar = np.where(grid > 0, 255, 0).ravel()
+    omap = range_libc.PyOMap(maps.OccupancyGrid.make(binar, 435, 350, colombia["resolution"], colombia["origin"]))
+    dist = orc.edt_float(colombia_scan["occ"])
+    return dict(omap=omap, rm=range_libc.PyRayMarchingGPU(omap, 300),
+                orc=orc.Marcher(dist, 300, colombia["resolution"], colombia["origin"]), dist=dist,
+                res=colombia["resolution"], origin=colombia["origin"])
+
+
+@pytest.fixture(scope="module")
+def big(orc):
+    omap, y, occ, dist = build_synth(orc, 2049, 1234)
+    return dict(omap=omap, rm=range_libc.PyRayMarchingGPU(omap, 300),
+                orc=orc.Marcher(dist, 300, y.resolution, y.origin), dist=dist, res=y.resolution,
+                origin=y.origin)
+
+
+def test_golden_fan(col, colombia_scan):
+    g = colombia_scan
+    out = np.zeros(g["fan"].size, np.float32)
+    col["rm"].calc_range_fan(g["poses"], out, FOV, 1080)
+    assert_ranges_match(out, g["fan"], col["res"])
+    # out-of-map / max_range beams are exactly max_range * scale
+    assert np.array_equal(out == np.float32(15.0), g["fan"] == np.float32(15.0))
+
+
+def test_golden_many_and_repeat_angles(col, colombia_scan):
+    g = colombia_scan
+    out = np.zeros(g["many"].size, np.float32)
+    col["rm"].calc_range_many(g["rays"], out)
+    assert_ranges_match(out, g["many"], col["res"])
+    out = np.zeros(g["rep"].size, np.float32)
+    col["rm"].calc_range_repeat_angles(g["poses"], g["angles"], out)
+    assert_ranges_match(out, g["rep"], col["res"])
+
+
+def test_survey_known_answer(col):
+    out = np.zeros(1080, np.float32)
+    ins = np.zeros((1080, 3), np.float32)
+    ins[0] = (0.275, 0.0, 0.0)
+    col["rm"].calc_range_many(ins, out, FOV, 1080)           # the fork's single-pose call
+    for j, v in {0: 1.2391100, 270: 1.1963634, 540: 3.7185178, 810: 1.8073667, 1079: 3.5077786}.items():
+        assert abs(out[j] - v) < 1e-6
+    assert abs(out.sum(dtype=np.float64) - 3282.2590) < 2e-2
+
+
+def test_fork_layout_ignores_dead_rows(col, colombia_scan):
+    poses = colombia_scan["poses"][:7]
+    wide = np.full((7 * 1080, 3), 77.0, np.float32)
+    wide[::1080] = poses
+    out = np.zeros(7 * 1080, np.float32)
+    col["rm"].calc_range_many(wide, out, FOV, 1080)
+    assert_ranges_match(out, colombia_scan["fan"][:7 * 1080], col["res"])
+
+
+@pytest.mark.parametrize("num_rays", [1, 31, 32, 33, 60, 270, 1080, 1081, 4097])
+def test_fan_ragged_beam_counts(col, num_rays):
+    poses = maps.sample_free_poses(col["dist"], 37, num_rays, col["res"], col["origin"])
+    out = np.full(37 * num_rays + 5, -1.0, np.float32)
+    col["rm"].calc_range_fan(poses, out[:37 * num_rays], FOV, num_rays)
+    assert_ranges_match(out[:37 * num_rays], col["orc"].calc_range_fan(poses, num_rays, FOV), col["res"],
+                        min_identical=0.995 if num_rays < 100 else 0.999)
+    assert np.all(out[37 * num_rays:] == -1.0)   # nothing written past the end
+
+
+def test_empty_batches(col):
+    col["rm"].calc_range_fan(np.zeros((0, 3), np.float32), np.zeros(0, np.float32), FOV, 1080)
+    col["rm"].calc_range_many(np.zeros((0, 3), np.float32), np.zeros(0, np.float32))
+    col["rm"].calc_range_repeat_angles(np.zeros((0, 3), np.float32), np.zeros(4, np.float32), np.zeros(0, np.float32))
+    col["rm"].calc_range_repeat_angles(np.zeros((3, 3), np.float32), np.zeros(0, np.float32), np.zeros(0, np.float32))
+
+
+def test_out_of_map_nan_and_inside_wall(col, orc):
+    rays = np.array([[-100.0, 0.0, 0.3], [1e9, 1e9, 0.0], [np.nan, 0.0, 0.0], [0.0, np.nan, 0.0],
+                     [0.275, 0.0, np.nan], [np.inf, 0.0, 0.0], [-5.70654, -2.020793, 0.5],
+                     [-5.70654 - 0.03, -2.020793 + 1.0, 0.0]], np.float32)
+    out = np.zeros(len(rays), np.float32)
+    col["rm"].calc_range_many(rays, out)
+    want = col["orc"].calc_range_many(rays)
+    assert np.array_equal(out, want), (out, want)
+    assert np.all(out[:6] == np.float32(15.0))
+
+
+def test_calc_range_single(col, colombia_scan):
+    p = colombia_scan["rays"][100]
+    assert col["rm"].calc_range(*p) == pytest.approx(float(colombia_scan["many"][100]), abs=1e-6)
+
+
+def test_mcts_rollout_batch_on_stand_in_map(big):
+    # BASELINE config 2 at reduced pose count: the oracle finishes in seconds
+    poses = maps.sample_free_poses(big["dist"], 512, 42, big["res"], big["origin"])
+    out = np.zeros(512 * 1080, np.float32)
+    big["rm"].calc_range_fan(poses, out, FOV, 1080)
+    want, steps = big["orc"].calc_range_fan(poses, 1080, FOV, steps=True, threads=0)
+    same = assert_ranges_match(out, want, big["res"])
+    print(f"config-2 slice: {same*100:.4f}% bit-identical, {steps.mean():.2f} steps/ray")
+
+
+def test_particle_filter_shape_repeat_angles(big):
+    # BASELINE config 3 shape: many poses x 60 angles
+    poses = maps.sample_free_poses(big["dist"], 20000, 43, big["res"], big["origin"])
+    angles = np.linspace(-FOV / 2, FOV / 2, 60, endpoint=False).astype(np.float32)
+    out = np.zeros(20000 * 60, np.float32)
+    big["rm"].calc_range_repeat_angles(poses, angles, out)
+    assert_ranges_match(out, big["orc"].calc_range_repeat_angles(poses, angles, threads=0), big["res"])
+
+
+def test_step_counter_matches_oracle(big):
+    poses = maps.sample_free_poses(big["dist"], 64, 44, big["res"], big["origin"])
+    out = np.zeros(64 * 1080, np.float32)
+    big["rm"].count_steps(True)
+    try:
+        big["rm"].calc_range_fan(poses, out, FOV, 1080)
+        got = big["rm"].last_steps()
+    finally:
+        big["rm"].count_steps(False)
+    _, steps = big["orc"].calc_range_fan(poses, 1080, FOV, steps=True)
+    assert abs(got - int(steps.sum())) <= 0.002 * steps.sum()
+
+
+def test_full_size_config2_properties(big):
+    # BASELINE config 2 at full size (4096 x 1080): size-independent properties + oracle parity
+    poses = maps.sample_free_poses(big["dist"], 4096, 45, big["res"], big["origin"])
+    out = np.zeros(4096 * 1080, np.float32)
+    big["rm"].calc_range_fan(poses, out, FOV, 1080)
+    assert np.all(np.isfinite(out)) and out.min() >= 0.0
+    assert out.max() <= 15.0 + 2 * 0.05 * 1.5           # hit ranges may exceed max_range slightly (A.6)
+    again = np.zeros_like(out)
+    big["rm"].calc_range_fan(poses, again, FOV, 1080)
+    assert np.array_equal(out, again)                    # deterministic
+    # a permutation of the poses permutes the scans
+    perm = np.random.default_rng(0).permutation(4096)
+    pout = np.zeros_like(out)
+    big["rm"].calc_range_fan(np.ascontiguousarray(poses[perm]), pout, FOV, 1080)
+    assert np.array_equal(pout.reshape(4096, 1080), out.reshape(4096, 1080)[perm])
+    want = big["orc"].calc_range_fan(poses, 1080, FOV, threads=0)
+    assert_ranges_match(out, want, big["res"])
+
+
+def test_torch_device_tensors_match_host_path(big):
+    import torch
+    poses = maps.sample_free_poses(big["dist"], 300, 46, big["res"], big["origin"])
+    host = np.zeros(300 * 1080, np.float32)
+    big["rm"].calc_range_fan(poses, host, FOV, 1080)
+    dp = torch.from_numpy(poses).cuda()
+    do = torch.zeros(300 * 1080, dtype=torch.float32, device="cuda")
+    big["rm"].calc_range_fan(dp, do, FOV, 1080)
+    assert np.array_equal(do.cpu().numpy(), host)
+    # upstream shapes on device too
+    wide = torch.zeros((300 * 1080, 3), dtype=torch.float32, device="cuda")
+    wide[::1080] = dp
+    do2 = torch.zeros_like(do)
+    big["rm"].calc_range_many(wide, do2, FOV, 1080)
+    assert torch.equal(do, do2)
+    rows = torch.from_numpy(poses).cuda()
+    o3 = torch.zeros(300, dtype=torch.float32, device="cuda")
+    big["rm"].calc_range_many(rows, o3)
+    h3 = np.zeros(300, np.float32)
+    big["rm"].calc_range_many(poses, h3)
+    assert np.array_equal(o3.cpu().numpy(), h3)
+    with pytest.raises(ValueError):
+        big["rm"].calc_range_fan(dp, host, FOV, 1080)     # mixed host/device
+    with pytest.raises(ValueError):
+        big["rm"].calc_range_fan(dp.double(), do, FOV, 1080)
+
+
+def test_rotated_origin_map(orc):
+    # non-zero origin yaw exercises the world->grid rotation (A.4)
+    rng = np.random.default_rng(8)
+    occ = np.zeros((200, 260), np.uint8)
+    occ[:3, :] = occ[-3:, :] = occ[:, :3] = occ[:, -3:] = 1
+    for _ in range(10):
+        r, c = rng.integers(10, 180), rng.integers(10, 240)
+        occ[r:r + 6, c:c + 9] = 1
+    origin = (1.5, -2.0, 0.6)
+    msg = maps.OccupancyGrid.make(np.where(occ, 100, 0).astype(np.int8).ravel(), 260, 200, 0.1, origin)
+    omap = range_libc.PyOMap(msg)
+    dist = orc.edt_float(occ)
+    assert np.array_equal(omap.dist(), dist)
+    rm = range_libc.PyRayMarching(omap, 150)
+    m = orc.Marcher(dist, 150, 0.1, origin)
+    # world poses: rotate grid-frame samples by +yaw about the origin
+    gx, gy = rng.uniform(20, 240, 400) * 0.1, rng.uniform(20, 180, 400) * 0.1
+    c, s = np.cos(0.6), np.sin(0.6)
+    rays = np.stack([origin[0] + c * gx - s * gy, origin[1] + s * gx + c * gy,
+                     rng.uniform(-np.pi, np.pi, 400)], axis=1).astype(np.float32)
+    out = np.zeros(400, np.float32)
+    rm.calc_range_many(rays, out)
+    assert_ranges_match(out, m.calc_range_many(rays), 0.1, min_identical=0.99)
