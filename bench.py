@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- rays/s of the batched lidar scan path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+A step is one pass of the hot path (the fork's 4-arg calc_range_many fan: scanMany) over one
+batch of synthetic poses.  At N=1 the workload is BASELINE.json configs[1]: 4096 poses x 1080
+beams (fov 4.71, max range 300 px) on the 2049^2 stand-in for the missing maps/map.pgm
+(synth_map(2049, 1234)).  For N>1 every rank marches its own 4096-pose
+shard against its own replica of the map (weak scaling) and the ranges are all-gathered over
+NCCL (--gather none to leave them sharded).
+
+One JSON line is printed by rank 0; keys follow the driver contract plus `roofline` and
+`cpu_baseline`.  `value` is device time (CUDA events per step on the launching stream, L2
+flushed between steps, max over ranks); `e2e` is the same metric through
+ScanSimulator2D.scanMany with host buffers (H2D + kernel + D2H per step, wall clock).
+`--impl reference` times the CPU oracle (the restated range_libc RayMarching; the original is
+not in the reference checkout) on all host threads instead.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FOV = 4.71
+MAX_RANGE_PX = 300
+MAP_N, MAP_SEED = 2049, 1234
+METRIC = "rays/sec"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--poses", type=int, default=4096, help="poses per GPU per step")
+    ap.add_argument("--beams", type=int, default=1080)
+    ap.add_argument("--gather", default="allgather", choices=["allgather", "none"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps")
+    return ap.parse_args()
+
+
+def workload_name(args):
+    return (f"MCTS rollout batch: {args.poses} poses x {args.beams} beams, fov {FOV}, max_range "
+            f"{MAX_RANGE_PX}px, synth_map({MAP_N},{MAP_SEED}) stand-in for maps/map.pgm")
+
+
+def build_map_cpu(oracle):
+    from pyracecarsimulator_b200 import maps
+    img = maps.synth_map(MAP_N, MAP_SEED)
+    y = maps.synth_yaml(MAP_N)
+    grid = oracle.mapserver_occupancy(img, y.negate, y.occupied_thresh, y.free_thresh)
+    occ = oracle.omap_from_grid(grid, True)
+    dist = oracle.sqrt_dist2(oracle.edt_exact(occ))
+    return y, dist
+
+
+def time_oracle(marcher, poses, beams, threads, reps):
+    out = np.empty(poses.shape[0] * beams, np.float32)
+    best = []
+    t_w = time.perf_counter()
+    while time.perf_counter() - t_w < (3.0 if threads != 1 else 0.5):   # let the host threads spread out
+        marcher.calc_range_fan(poses, beams, FOV, outs=out, threads=threads)
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        marcher.calc_range_fan(poses, beams, FOV, outs=out, threads=threads)
+        best.append(time.perf_counter() - t0)
+    return float(np.median(best)), out
+
+
+# ------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    import oracle
+    from pyracecarsimulator_b200 import maps
+    y, dist = build_map_cpu(oracle)
+    m = oracle.Marcher(dist, MAX_RANGE_PX, y.resolution, y.origin)
+    cores = oracle.max_threads()
+    sample_poses = min(args.poses, 512)
+    poses = maps.sample_free_poses(dist, sample_poses, 4242, y.resolution, y.origin)
+    out = np.empty(sample_poses * args.beams, np.float32)
+    # host threads on these VMs take a second or two of sustained load to spread over the cores
+    t_w, n_w = time.perf_counter(), 0
+    while n_w < max(1, args.warmup) or time.perf_counter() - t_w < 3.0:
+        m.calc_range_fan(poses, args.beams, FOV, outs=out, threads=0)
+        n_w += 1
+    steps = max(1, min(args.steps, 50))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        m.calc_range_fan(poses, args.beams, FOV, outs=out, threads=0)
+    dt = time.perf_counter() - t0
+    rays = sample_poses * args.beams * steps
+    value = rays / dt
+    sample = f"{sample_poses} of {args.poses} poses x {args.beams} beams per step, {steps} steps"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args), "host_threads": cores,
+                   "implementation": "oracle/rangelib_oracle.c (CPU restatement of range_libc "
+                                     "RayMarching; range_libc itself is not in the reference checkout)"},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Polls NVML for SM clock and throttle reasons while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def result(self):
+        self.stop_flag = True
+        if self.is_alive():
+            self.join(timeout=1.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------- native arm
+def run_native(args, rank, world, local_rank):
+    import torch
+    from pyracecarsimulator_b200 import _native, maps, range_libc
+    from pyracecarsimulator_b200.scan_simulator import ScanSimulator2D
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the native arm has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist_on = world > 1
+    if dist_on:
+        import torch.distributed as tdist
+        tdist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist_on:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- map replica on this GPU (ingest kernels), poses for this rank's shard ----
+    img = maps.synth_map(MAP_N, MAP_SEED)
+    y = maps.synth_yaml(MAP_N)
+    path = f"/tmp/_rl_bench_map_{os.getpid()}.pgm"
+    maps.write_pgm(path, img)
+    y.image = path
+    omap = range_libc.PyOMap(y, device=local_rank)
+    os.unlink(path)
+    dist_field = omap.dist()
+    P, B = args.poses, args.beams
+    n_rays = P * B
+    n_sets = 4  # rotate pose batches so consecutive steps do not repeat the same rays
+    pose_sets = [maps.sample_free_poses(dist_field, P, 1000 + 17 * rank + s, y.resolution, y.origin)
+                 for s in range(n_sets)]
+    d_poses = [torch.from_numpy(p).to(dev) for p in pose_sets]
+    d_out = torch.empty(n_rays, dtype=torch.float32, device=dev)
+    d_all = torch.empty(world * n_rays, dtype=torch.float32, device=dev) if dist_on and args.gather == "allgather" else None
+    rm = range_libc.PyRayMarchingGPU(omap, MAX_RANGE_PX)
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(i, ev0=None, ev1=None):
+        if flush is not None:
+            flush.fill_(i & 0xFF)          # 256 MiB write > 126 MB L2: evicts the distance field
+        if ev0 is not None:
+            ev0.record()
+        rm.calc_range_fan(d_poses[i % n_sets], d_out, FOV, B)
+        if d_all is not None:
+            tdist.all_gather_into_tensor(d_all, d_out)
+        if ev1 is not None:
+            ev1.record()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    K = args.steps
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(K):
+        step(i, *ev[i])
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = K  # one march kernel per step (flush fills and NCCL kernels are not ours)
+
+    # ---- e2e through the reference-facing API with host buffers ----
+    sim = ScanSimulator2D(B, FOV, 0.01, batch_size=P)
+    sim.setMap(omap, MAX_RANGE_PX, y.resolution, y.origin)
+    sim.setRaytracingMethod("RMGPU")
+    for i in range(3):
+        sim.scanMany(pose_sets[i % n_sets])
+    e2e_steps = max(3, min(K, 50))
+    barrier()
+    t0 = time.perf_counter()
+    checksum = 0.0
+    for i in range(e2e_steps):
+        out = sim.scanMany(pose_sets[i % n_sets])
+        checksum += float(out[0])
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.result()
+
+    # ---- max over ranks ----
+    t = torch.tensor([dev_ms, e2e_s, t_wall], dtype=torch.float64, device=dev)
+    if dist_on:
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+    dev_ms, e2e_s, t_wall = (float(v) for v in t.tolist())
+
+    if rank == 0:
+        # ---- roofline inputs: algorithmic bytes of ONE launch (4 B/step + 4 B/ray + 12 B/pose) ----
+        rm.count_steps(True)
+        steps_per_set = []
+        for s in range(n_sets):
+            rm.calc_range_fan(d_poses[s], d_out, FOV, B)
+            steps_per_set.append(rm.last_steps())
+        rm.count_steps(False)
+        mean_steps = float(np.mean(steps_per_set))
+        alg_bytes = 4.0 * mean_steps + 4.0 * n_rays + 12.0 * P
+        # kernel-only time: same loop, gather off, events around the launch alone
+        k_ms = []
+        for i in range(min(K, 50)):
+            if flush is not None:
+                flush.fill_(i & 0xFF)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            rm.calc_range_fan(d_poses[i % n_sets], d_out, FOV, B)
+            b.record()
+            k_ms.append((a, b))
+        torch.cuda.synchronize()
+        kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ms]))
+        warm_ms = []
+        for i in range(min(K, 50)):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            rm.calc_range_fan(d_poses[i % n_sets], d_out, FOV, B)
+            b.record()
+            warm_ms.append((a, b))
+        torch.cuda.synchronize()
+        warm_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in warm_ms]))
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            hbm_peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+        else:
+            hbm_peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        gather_gbs = _native.gather_bandwidth(local_rank, dist_field.nbytes, 64, 10)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                    "kernel": "march_pose_kernel<FAN>", "kernel_ms": kernel_ms,
+                    "kernel_ms_warm_l2": warm_kernel_ms,
+                    "algorithmic_bytes_per_launch": alg_bytes, "march_steps_per_ray": mean_steps / n_rays,
+                    "note": "the march is an L2-resident gather, not an HBM stream; l2_gather is the bound "
+                            "BASELINE.json names",
+                    "l2_gather": {"achieved": achieved, "peak": gather_gbs, "unit": "GB/s",
+                                  "frac": achieved / gather_gbs,
+                                  "peak_source": "rl_gather_bandwidth: random 4-B gathers from a "
+                                                 f"{dist_field.nbytes >> 20} MiB L2-resident buffer, measured live"}}
+
+        cpu_baseline = None
+        if not args.no_cpu_baseline and world == 1:
+            import oracle
+            m = oracle.Marcher(dist_field, MAX_RANGE_PX, y.resolution, y.origin)
+            cores = oracle.max_threads()
+            n1 = min(P, 256)
+            t1, ref1 = time_oracle(m, pose_sets[0][:n1], B, 1, 3)
+            tn, refn = time_oracle(m, pose_sets[0], B, 0, 3)
+            rm.calc_range_fan(d_poses[0], d_out, FOV, B)
+            got = d_out.cpu().numpy()
+            tol = np.maximum(1e-4 * np.abs(refn), 0.5 * y.resolution)
+            cpu_baseline = {"value": n_rays / tn, "unit": "rays/s", "cores": cores, "kind": "port",
+                            "sample": f"{P} poses x {B} beams (one full step), all {cores} host threads, median of 3; "
+                                      f"single thread on {n1} poses: {n1 * B / t1:.4g} rays/s",
+                            "single_thread_value": n1 * B / t1,
+                            "parity_vs_gpu": {"bit_identical_frac": float(np.mean(got == refn)),
+                                              "within_tolerance": bool(np.all(np.abs(got - refn) <= tol))}}
+
+        total_rays = world * n_rays
+        line = {
+            "metric": METRIC, "value": total_rays * K / (dev_ms * 1e-3), "unit": "rays/s", "n_gpus": world,
+            "steps": K, "warmup": args.warmup, "ms_per_step": dev_ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "poses_per_gpu": P, "beams": B,
+                       "global_rays_per_step": total_rays, "map": f"{MAP_N}x{MAP_N} fp32 distance field "
+                       f"({dist_field.nbytes >> 20} MiB, replicated per GPU)",
+                       "parallelism": f"pose-sharded x{world}, map replicated" +
+                                      (", NCCL all_gather of ranges inside the step" if d_all is not None else ""),
+                       "l2": "no flush" if args.no_flush else "flushed between steps (256 MiB fill), fill excluded from the per-step events",
+                       "timing": "CUDA events per step on the launching stream, summed, max over ranks",
+                       "trig": "exact (sincosf per beam)"},
+            "wall_ms_per_step_incl_flush": t_wall / K * 1e3,
+            "e2e": {"value": total_rays * e2e_steps / e2e_s, "unit": "rays/s",
+                    "h2d_bytes_per_step": P * 12, "d2h_bytes_per_step": n_rays * 4, "steps": e2e_steps,
+                    "api": "ScanSimulator2D.scanMany(host poses) -> host ranges (pinned), per rank"},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "ingest_ms": omap.ingest_ms,
+        }
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line))
+    if dist_on:
+        tdist.barrier()
+        tdist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        import subprocess
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_native(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

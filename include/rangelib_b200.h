@@ -143,6 +143,16 @@ RL_API int32_t rl_calc_range_repeat_angles_host(rl_marcher *m, const float *pose
 RL_API int32_t rl_marcher_count_steps(rl_marcher *m, int32_t enable);
 RL_API int32_t rl_marcher_last_steps(rl_marcher *m, uint64_t *steps);
 
+/* ---- measurement support (not on the product path) ---- */
+/* Throughput, in GB/s at 4 bytes per gather, of independent random 4-byte gathers from a    */
+/* `buffer_bytes` L2-resident buffer: the denominator of the L2-gather roofline.             */
+RL_API int32_t rl_gather_bandwidth(int32_t device, int64_t buffer_bytes, int32_t rounds, int32_t iters,
+                                   float *gbytes_per_s);
+
+/* The device's sinf/cosf (glibc's algorithm, csrc/glibc_trig.cuh) over an array on the      */
+/* current device, for the parity tests: d_sin[i] = sinf(d_in[i]), d_cos[i] = cosf(d_in[i]). */
+RL_API int32_t rl_probe_sincosf(const float *d_in, float *d_sin, float *d_cos, int64_t n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,7 +29,7 @@ i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 def build(force=False):
     """Compile liboracle.so (and _ref/ when /root/reference is present)."""
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("rangelib_oracle.c", "car_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("rangelib_oracle.c", "car_oracle.c", "trig_twin.c")]
     stale = force or not os.path.exists(so) or any(
         os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     ref_so = os.path.join(_HERE, "_ref", "libracecar_ref.so")
@@ -82,6 +82,9 @@ def lib():
     L.orc_calc_range_repeat_angles.argtypes = [C.c_void_p, f32p, f32p, f32p, C.c_int64, C.c_int,
                                                C.c_void_p, C.c_int]
     L.orc_max_threads.restype = C.c_int
+    L.orc_twin_sincosf.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.orc_twin_mismatches.restype = C.c_uint64
+    L.orc_twin_mismatches.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64]
     L.orc_car_step.argtypes = [C.POINTER(CarParams), f64p, C.c_double, C.c_double, C.c_double]
     L.orc_car_scan_pose.argtypes = [f64p, C.c_double, f64p]
     L.orc_car_edge_distances.argtypes = [C.POINTER(CarParams), C.c_int, C.c_double, C.c_double,
@@ -186,6 +189,17 @@ class Marcher:
         s, sp = self._steps(n * a, steps)
         lib().orc_calc_range_repeat_angles(self._h, ins, angles, outs, n, a, sp, threads)
         return (outs, s) if steps else outs
+
+
+def twin_sincosf(y):
+    """(sin, cos) from the C twin of the device's glibc-compatible sincosf."""
+    s, c = C.c_float(), C.c_float()
+    lib().orc_twin_sincosf(float(y), C.byref(s), C.byref(c))
+    return s.value, c.value
+
+
+def twin_mismatches(start, stride, count):
+    return int(lib().orc_twin_mismatches(start, stride, count))
 
 
 def max_threads():

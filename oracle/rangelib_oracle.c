@@ -315,6 +315,36 @@ ORC_EXPORT int orc_max_threads(void)
     return n > 0 ? (int)n : 1;
 }
 
+/* Persistent worker pool: threads are created once and parked on a condition variable, so a  */
+/* short call does not pay thread start-up and CPU migration every time.                       */
+static struct {
+    pthread_mutex_t mu;
+    pthread_cond_t start, done;
+    pthread_t tid[256];
+    int n;                 /* workers created */
+    unsigned long gen;     /* job generation */
+    orc_job *job;
+    int want, pending;     /* workers that should take part / still running */
+} pool = { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, {0}, 0, 0, NULL, 0, 0 };
+
+static void *pool_main(void *arg)
+{
+    const int me = (int)(intptr_t)arg;
+    unsigned long seen = 0;
+    pthread_mutex_lock(&pool.mu);
+    for (;;) {
+        while (pool.gen == seen) pthread_cond_wait(&pool.start, &pool.mu);
+        seen = pool.gen;
+        if (me >= pool.want) continue;
+        orc_job *j = pool.job;
+        pthread_mutex_unlock(&pool.mu);
+        orc_worker(j);
+        pthread_mutex_lock(&pool.mu);
+        if (--pool.pending == 0) pthread_cond_signal(&pool.done);
+    }
+    return NULL;
+}
+
 /* threads: 1 = caller's thread only (upstream's loop is single-threaded); 0 = all cores */
 static void orc_parallel_for(int64_t n, int64_t chunk, int threads, orc_body body, void *ctx)
 {
@@ -323,15 +353,25 @@ static void orc_parallel_for(int64_t n, int64_t chunk, int threads, orc_body bod
     if (threads == 1 || n <= chunk) { body(ctx, 0, n); return; }
     int64_t next = 0;
     orc_job job = { body, ctx, n, chunk, &next };
-    pthread_t tid[256];
-    int started = 0;
-    for (int i = 0; i < threads - 1; ++i)
-        if (pthread_create(&tid[started], NULL, orc_worker, &job) == 0) ++started;
+    pthread_mutex_lock(&pool.mu);
+    while (pool.n < threads - 1) {
+        if (pthread_create(&pool.tid[pool.n], NULL, pool_main, (void *)(intptr_t)pool.n) != 0) break;
+        pthread_detach(pool.tid[pool.n]);
+        ++pool.n;
+    }
+    const int helpers = pool.n < threads - 1 ? pool.n : threads - 1;
+    pool.job = &job;
+    pool.want = helpers;
+    pool.pending = helpers;
+    ++pool.gen;
+    pthread_cond_broadcast(&pool.start);
+    pthread_mutex_unlock(&pool.mu);
     orc_worker(&job);
-    for (int i = 0; i < started; ++i) pthread_join(tid[i], NULL);
+    pthread_mutex_lock(&pool.mu);
+    while (pool.pending > 0) pthread_cond_wait(&pool.done, &pool.mu);
+    pthread_mutex_unlock(&pool.mu);
 }
 
-/* 2-arg calc_range_many: one (x, y, theta) row per ray (scripts/two_player/scan.py:69-70). */
 typedef struct {
     const orc_marcher *m; const float *ins; const float *angles; float *outs; int32_t *steps;
     int num_rays; float fov; int64_t pose_stride_rows;

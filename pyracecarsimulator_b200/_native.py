@@ -60,6 +60,8 @@ SIGNATURES = {
     "rl_calc_range_repeat_angles_host": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32]),
     "rl_marcher_count_steps": (_i32, [_vp, _i32]),
     "rl_marcher_last_steps": (_i32, [_vp, C.POINTER(C.c_uint64)]),
+    "rl_probe_sincosf": (_i32, [_vp, _vp, _vp, _i64, _vp]),
+    "rl_gather_bandwidth": (_i32, [_i32, _i64, _i32, _i32, C.POINTER(_f)]),
 }
 
 
@@ -97,6 +99,13 @@ def check(rc: int, what: str = "") -> None:
     if rc == RL_ERR_OOM:
         raise MemoryError(msg)
     raise RuntimeError(msg)
+
+
+def gather_bandwidth(device: int, buffer_bytes: int, rounds: int = 64, iters: int = 10) -> float:
+    """GB/s (4 B per gather) of random gathers from an L2-resident buffer of this size."""
+    v = _f()
+    check(lib().rl_gather_bandwidth(device, buffer_bytes, rounds, iters, C.byref(v)), "gather_bandwidth")
+    return float(v.value)
 
 
 def device_count() -> int:

@@ -1,0 +1,71 @@
+// calib.cu -- the denominator of the L2-gather roofline:
+// throughput of independent random 4-byte gathers from a distance-field-sized, L2-resident
+// buffer on this GPU.  Every march step is one such gather; nothing here is on the product path.
+#include "common.h"
+
+namespace {
+
+constexpr int ILP = 8;
+
+__global__ void __launch_bounds__(256)
+gather_kernel(const float *__restrict__ buf, uint32_t n, int rounds, float *__restrict__ sink)
+{
+    uint32_t s[ILP];
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s[i] = (tid * ILP + i) * 2654435761u + 12345u;
+    float acc = 0.f;
+    for (int r = 0; r < rounds; ++r) {
+        float v[ILP];
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) {
+            s[i] = s[i] * 1664525u + 1013904223u;
+            const uint32_t idx = (uint32_t)(((uint64_t)s[i] * n) >> 32);
+            v[i] = __ldg(buf + idx);
+        }
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) acc += v[i];
+    }
+    if (acc == 1234.5678f) sink[0] = acc;  // keep the loads alive
+}
+
+}  // namespace
+
+extern "C" RL_API int32_t rl_gather_bandwidth(int32_t device, int64_t buffer_bytes, int32_t rounds,
+                                       int32_t iters, float *gbytes_per_s)
+{
+    if (!gbytes_per_s || buffer_bytes < 4096 || rounds <= 0 || iters <= 0)
+        return rl::fail(RL_ERR_BAD_ARG, "rl_gather_bandwidth: bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+        return rl::fail(RL_ERR_NO_DEVICE, "rl_gather_bandwidth: no such CUDA device");
+    rl::DeviceGuard guard(device);
+    const uint32_t n = (uint32_t)(buffer_bytes / 4);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    float *buf = nullptr, *sink = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t e = cudaMalloc(&buf, (size_t)n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&sink, 4);
+    if (e == cudaSuccess) e = cudaMemset(buf, 0, (size_t)n * 4);
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    const int blocks = sms * 8;  // 8 CTAs x 256 threads = 64 resident warps per SM
+    float ms = 0.f;
+    if (e == cudaSuccess) {
+        gather_kernel<<<blocks, 256>>>(buf, n, rounds, sink);  // warm-up: pulls the buffer into L2
+        cudaEventRecord(e0, 0);
+        for (int i = 0; i < iters; ++i) gather_kernel<<<blocks, 256>>>(buf, n, rounds, sink);
+        cudaEventRecord(e1, 0);
+        e = cudaEventSynchronize(e1);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        if (e == cudaSuccess) e = cudaGetLastError();
+    }
+    cudaFree(buf); cudaFree(sink);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (e != cudaSuccess) return rl::fail(RL_ERR_CUDA, std::string("rl_gather_bandwidth: ") + cudaGetErrorString(e));
+    const double gathers = (double)blocks * 256 * ILP * rounds * iters;
+    *gbytes_per_s = (float)(gathers * 4.0 / (ms * 1e-3) / 1e9);
+    return RL_OK;
+}

