@@ -76,6 +76,7 @@ typedef enum rl_status {
 
 typedef struct rl_map rl_map;
 typedef struct rl_marcher rl_marcher;
+typedef struct rl_car rl_car;
 
 RL_API int32_t rl_abi_version(void);
 RL_API const char *rl_last_error(void);
@@ -142,6 +143,45 @@ RL_API int32_t rl_calc_range_repeat_angles_host(rl_marcher *m, const float *pose
 /* marcher was asked to count them (rl_marcher_count_steps(m, 1)); used by the roofline.    */
 RL_API int32_t rl_marcher_count_steps(rl_marcher *m, int32_t enable);
 RL_API int32_t rl_marcher_last_steps(rl_marcher *m, uint64_t *steps);
+
+/* ---- vehicle model, crash test and fused rollout (north_star (c)) ---- */
+
+/* params17: the 17 doubles of the reference Car constructor, in its order                     */
+/* (racecar/src/racecar.cpp:10-13): WB, FC, H_CG, L_F, L_R, CS_F, CS_R, MASS, I_Z, CRASH_THRESH, */
+/* WIDTH, LENGTH, MAX_STEER_VEL, MAX_STEER_ANG, MAX_SPEED, MAX_ACCEL, MAX_DECEL.               */
+RL_API int32_t rl_car_create(const double *params17, int32_t device, rl_car **out);
+RL_API int32_t rl_car_destroy(rl_car *car);
+/* Car::setCarEdgeDistances (racecar.cpp:239-292): fixes the beam count of every later call. */
+RL_API int32_t rl_car_set_edge_distances(rl_car *car, int32_t num_rays, double min_ang, double ang_inc,
+                                         double scan_dist_to_base);
+RL_API int32_t rl_car_get_edge_distances(const rl_car *car, double *out, int32_t num_rays);
+/* Batched Car::control + Car::updatePosition (racecar.cpp:53-98, :294-303): d_states is        */
+/* (n_cars, 11) fp64 in the reference's getState layout, updated in place.                     */
+RL_API int32_t rl_car_step(rl_car *car, double *d_states, const double *d_speed, const double *d_steer,
+                           int64_t n_cars, double dt, void *stream);
+/* Car::isCrashed (racecar.cpp:305-328) over existing ranges, `groups` independent batches of   */
+/* `poses_per_group` scans: d_first[g] = first crashed pose (0-based) or -(poses_per_group+1). */
+RL_API int32_t rl_is_crashed(rl_car *car, const float *d_rays, int64_t groups, int32_t poses_per_group,
+                             int32_t *d_first, void *stream);
+/* RacecarSimulator.checkCollisionMany (scripts/racecar_simulator_v2.py:146-167): fan scan of   */
+/* d_poses (groups*poses_per_group, 3) with the crash test as the march epilogue.  d_ranges may */
+/* be NULL: then no range is written and poses after a group's first crash are skipped.        */
+RL_API int32_t rl_scan_crash(rl_marcher *m, rl_car *car, const float *d_poses, int64_t groups,
+                             int32_t poses_per_group, float fov, int32_t *d_first, float *d_ranges,
+                             void *stream);
+/* MCTS.rollout (scripts/mcts.py:202-245) for n_cars cars without leaving the GPU: `steps`       */
+/* updatePosition(dt), a new (speed, steer) from d_actions (n_cars, ceil(steps/action_every), 2) */
+/* every action_every-th step, a fan scan after every step from the base-link pose               */
+/* (lidar_pose = 0, what mcts.py:228-231 records) or the lidar pose (lidar_pose = 1,             */
+/* Car::getScanPose), crash test per scan.  d_crash_index[c] = first crashed step or             */
+/* -(steps+1); d_reward[c] (nullable) = sum of post-step velocities before the crash.            */
+/* d_poses (steps, n_cars, 3) fp32 and d_vsum (n_cars, steps) fp64 are caller-provided scratch   */
+/* that double as outputs (scanned poses, step-major; running velocity sums).                    */
+RL_API int32_t rl_rollout(rl_marcher *m, rl_car *car, double *d_states, const double *d_actions,
+                          int64_t n_cars, int32_t steps, int32_t action_every, double dt,
+                          int32_t lidar_pose, double scan_dist_to_base, float fov,
+                          int32_t *d_crash_index, double *d_reward, float *d_poses, double *d_vsum,
+                          void *stream);
 
 /* ---- measurement support (not on the product path) ---- */
 /* Throughput, in GB/s at 4 bytes per gather, of independent random 4-byte gathers from a    */

@@ -60,6 +60,14 @@ SIGNATURES = {
     "rl_calc_range_repeat_angles_host": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32]),
     "rl_marcher_count_steps": (_i32, [_vp, _i32]),
     "rl_marcher_last_steps": (_i32, [_vp, C.POINTER(C.c_uint64)]),
+    "rl_car_create": (_i32, [_vp, _i32, C.POINTER(_vp)]),
+    "rl_car_destroy": (_i32, [_vp]),
+    "rl_car_set_edge_distances": (_i32, [_vp, _i32, _d, _d, _d]),
+    "rl_car_get_edge_distances": (_i32, [_vp, _vp, _i32]),
+    "rl_car_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _d, _vp]),
+    "rl_is_crashed": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "rl_scan_crash": (_i32, [_vp, _vp, _vp, _i64, _i32, _f, _vp, _vp, _vp]),
+    "rl_rollout": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _d, _i32, _d, _f, _vp, _vp, _vp, _vp, _vp]),
     "rl_probe_sincosf": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "rl_gather_bandwidth": (_i32, [_i32, _i64, _i32, _i32, C.POINTER(_f)]),
 }

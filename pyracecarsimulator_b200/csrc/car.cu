@@ -1,0 +1,423 @@
+// car.cu -- the vehicle-model half of the fused rollout (north_star (c)) and the crash test that
+// follows every scan in the reference:
+//   Car::updatePosition / computeFromInput / updateNormal / updateSingle   racecar/src/racecar.cpp:53-237
+//   Car::getScanPose                                                       racecar/src/racecar.cpp:378-387
+//   Car::setCarEdgeDistances                                               racecar/src/racecar.cpp:239-292
+//   Car::isCrashed                                                         racecar/src/racecar.cpp:305-328
+//   MCTS.rollout (steps, action every 10th step, checkCollisionMany)       scripts/mcts.py:202-245
+// State layout is the reference's 11 doubles (racecar.cpp:330-376).  Everything is fp64 like the
+// reference; compiled with -fmad=false so products and sums round separately, as they do in the
+// reference built without -ffast-math (the oracle's build).  Device cos/sin/tan are CUDA's, which
+// may differ from the host libm in the last ulp: state parity is to a stated tolerance, the crash
+// test itself is exact on identical ranges.
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "glibc_trig.cuh"
+#include "march.cuh"
+
+struct rl_marcher;
+namespace rl {
+const MarchParams &marcher_params(const rl_marcher *m);
+int marcher_device(const rl_marcher *m);
+}  // namespace rl
+
+struct CarParams {
+    double wb, fc, h_cg, l_f, l_r, cs_f, cs_r, mass, i_z, crash_thresh, width, length;
+    double max_steer_vel, max_steer_ang, max_speed, max_accel, max_decel;
+};
+
+struct rl_car {
+    CarParams p{};
+    int device = 0;
+    int num_rays = 0;
+    std::vector<double> edge;   // host copy (computed with the host libm, like the reference)
+    double *d_edge = nullptr;
+    int32_t *d_first = nullptr; // scratch for *_host variants
+    size_t cap_first = 0;
+};
+
+namespace {
+
+constexpr double K_THRESH = 0.5, ST_THRESH = 0.53, GRAV = 9.81;
+constexpr double REF_PI = 3.145;  // sic: racecar/include/racecar.hpp:117
+constexpr int NO_CRASH = 0x7fffffff;
+
+__device__ __forceinline__ double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+
+// One Car::updatePosition(dt) on a register-resident state.
+struct CarState { double x, y, th, v, sa, w, beta, travel, total_v; int dyn, count; };
+
+__device__ __forceinline__ void car_update(const CarParams &p, CarState &s, double in_speed,
+                                           double in_steer, double dt)
+{
+    // computeFromInput (racecar.cpp:118-169)
+    const double kp = 2.0 * p.max_accel / p.max_speed;
+    const double dv = in_speed - s.v;
+    double accel;
+    if (s.v > 0) accel = (dv > 0) ? clampd(kp * dv, -p.max_accel, p.max_accel) : -p.max_decel;
+    else accel = (dv > 0) ? p.max_decel : clampd(kp * dv, -p.max_accel, p.max_accel);
+    const double ds = in_steer - s.sa;
+    double sv = 0.0;
+    if (fabs(ds) > 0.0001) sv = (ds > 0) ? p.max_steer_vel : -p.max_steer_vel;
+
+    const double px = s.x, py = s.y;
+    const double thresh = s.dyn ? ST_THRESH : K_THRESH;
+    if (s.v < thresh) {   // updateNormal (racecar.cpp:171-194)
+        const double xd = s.v * cos(s.th), yd = s.v * sin(s.th);
+        const double thd = s.v / p.wb * tan(s.sa);
+        s.x += xd * dt; s.y += yd * dt; s.th += thd * dt;
+        s.v += accel * dt; s.sa += sv * dt;
+        s.w = 0; s.beta = 0; s.dyn = 0;
+    } else {              // updateSingle (racecar.cpp:196-237)
+        const double xd = s.v * cos(s.th + s.beta), yd = s.v * sin(s.th + s.beta);
+        const double thd = s.w;
+        const double rv = GRAV * p.l_r - accel * p.h_cg;
+        const double fv = GRAV * p.l_f + accel * p.h_cg;
+        const double ratio = s.w / s.v;
+        const double first = p.fc / (s.v * (p.l_r + p.l_f));
+        const double wdd = (p.fc * p.mass / (p.i_z * p.wb)) *
+                           (p.l_f * p.cs_f * s.sa * rv + s.beta * (p.l_r * p.cs_r * fv - p.l_f * p.cs_f * rv) -
+                            ratio * ((p.l_f * p.l_f) * p.cs_f * rv + (p.l_r * p.l_r) * p.cs_r * fv));
+        const double bd = first * (p.cs_f * s.sa * (rv) - s.beta * (p.cs_r * fv + p.cs_f * rv) +
+                                   ratio * (p.cs_r * p.l_r * fv - p.cs_f * p.l_f * rv)) - s.w;
+        s.x += xd * dt; s.y += yd * dt; s.th += thd * dt;
+        s.v += accel * dt; s.sa += sv * dt;
+        s.w += wdd * dt; s.beta += bd * dt; s.dyn = 1;
+    }
+    const double ddx = px - s.x, ddy = py - s.y;
+    s.travel += sqrt(ddx * ddx + ddy * ddy);
+    s.total_v += s.v;
+    s.count += 1;
+    s.v = clampd(s.v, -p.max_speed, p.max_speed);
+    s.sa = clampd(s.sa, -p.max_steer_ang, p.max_steer_ang);
+}
+
+__device__ __forceinline__ CarState load_state(const double *st)
+{
+    CarState s;
+    s.x = st[0]; s.y = st[1]; s.th = st[2]; s.v = st[3]; s.sa = st[4]; s.w = st[5]; s.beta = st[6];
+    s.dyn = st[7] > 0.0; s.travel = st[8]; s.total_v = st[9]; s.count = (int)st[10];
+    return s;
+}
+
+__device__ __forceinline__ void store_state(double *st, const CarState &s)
+{
+    st[0] = s.x; st[1] = s.y; st[2] = s.th; st[3] = s.v; st[4] = s.sa; st[5] = s.w; st[6] = s.beta;
+    st[7] = s.dyn ? 1.0 : 0.0; st[8] = s.travel; st[9] = s.total_v; st[10] = (double)s.count;
+}
+
+// T updatePosition steps per car; a new (speed, steer) target every `action_every` steps
+// (scripts/mcts.py:216-222).  Records the pose scanned after every step, narrowed to fp32 exactly
+// where the reference narrows it (the f32 pose buffer, scripts/mcts.py:211, :229-231), and the
+// running sum of the post-step velocities (the rollout reward, scripts/mcts.py:235).
+__global__ void __launch_bounds__(128)
+car_rollout_kernel(CarParams p, double *__restrict__ states, const double *__restrict__ actions,
+                   int64_t n_cars, int steps, int action_every, double dt, int lidar_pose,
+                   double scan_dist, float *__restrict__ poses, double *__restrict__ vsum)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cars) return;
+    CarState s = load_state(states + 11 * c);
+    const int n_actions = (steps + action_every - 1) / action_every;
+    const double *act = actions + 2 * n_actions * c;
+    double speed = 0.0, steer = 0.0, acc = 0.0;
+    for (int i = 0; i < steps; ++i) {
+        if (i % action_every == 0) { speed = act[2 * (i / action_every)]; steer = act[2 * (i / action_every) + 1]; }
+        car_update(p, s, speed, steer, dt);
+        float *o = poses + 3 * ((int64_t)i * n_cars + c);   // step-major: all cars' step i are contiguous
+        if (lidar_pose) {   // Car::getScanPose
+            o[0] = (float)(s.x + scan_dist * cos(s.th));
+            o[1] = (float)(s.y + scan_dist * sin(s.th));
+        } else {            // base link, as MCTS.rollout records it
+            o[0] = (float)s.x;
+            o[1] = (float)s.y;
+        }
+        o[2] = (float)s.th;
+        acc += s.v;
+        vsum[c * steps + i] = acc;
+    }
+    store_state(states + 11 * c, s);
+}
+
+// Batched Car::control + Car::updatePosition: one step, per-car targets.
+__global__ void __launch_bounds__(128)
+car_step_kernel(CarParams p, double *__restrict__ states, const double *__restrict__ speed,
+                const double *__restrict__ steer, int64_t n_cars, double dt)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cars) return;
+    CarState s = load_state(states + 11 * c);
+    car_update(p, s, speed[c], steer[c], dt);
+    store_state(states + 11 * c, s);
+}
+
+__global__ void fill_i32_kernel(int32_t *p, int64_t n, int32_t v)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// first[g] : NO_CRASH -> -(poses_per_group + 1), Car::isCrashed's "no crash" value
+__global__ void finalize_first_kernel(int32_t *first, int64_t groups, int poses_per_group,
+                                      const double *__restrict__ vsum, double *__restrict__ reward)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= groups) return;
+    int32_t f = first[g];
+    if (f == NO_CRASH) f = -(poses_per_group + 1);
+    first[g] = f;
+    if (reward) {   // sum(rewards[:index]) if index >= 0 else sum(rewards)   (scripts/mcts.py:240-245)
+        const int upto = f < 0 ? poses_per_group : f;
+        reward[g] = upto > 0 ? vsum[g * poses_per_group + upto - 1] : 0.0;
+    }
+}
+
+// Car::isCrashed over ranges that already exist: ray i of pose k of group g.
+__global__ void __launch_bounds__(256)
+crash_from_rays_kernel(const float *__restrict__ rays, const double *__restrict__ edge, int64_t total,
+                       int num_rays, int poses_per_group, double thresh, int32_t *first)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int64_t k = i / num_rays;
+    const int j = (int)(i - k * num_rays);
+    if (((double)rays[i] - edge[j]) < thresh) {
+        const int64_t g = k / poses_per_group;
+        atomicMin(first + g, (int)(k - g * poses_per_group));
+    }
+}
+
+// Fan march with the crash test as its epilogue.  WRITE: also store the ranges.  Without WRITE a
+// ray whose group already crashed at an earlier pose is skipped (it cannot change the minimum).
+// Pose order: group-major (pose k = g*poses_per_group + p, the scanMany layout) or step-major
+// (k = p*groups + g, used by the rollout so that a car's earlier steps are scanned -- and its crash
+// known -- long before its later steps are scheduled).
+template <bool WRITE, bool STEP_MAJOR>
+__global__ void __launch_bounds__(256)
+march_crash_kernel(rl::MarchParams P, const float *__restrict__ poses, const double *__restrict__ edge,
+                   int64_t total, int num_rays, int poses_per_group, int64_t groups, float fov, float inc,
+                   double thresh, int32_t *first, float *__restrict__ outs)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int64_t k;
+    int j;
+    if (total <= 0xffffffffLL) {
+        const uint32_t k32 = (uint32_t)i / (uint32_t)num_rays;
+        k = k32;
+        j = (int)((uint32_t)i - k32 * (uint32_t)num_rays);
+    } else {
+        k = i / num_rays;
+        j = (int)(i - k * num_rays);
+    }
+    int64_t g;
+    int pose_in_group;
+    if (STEP_MAJOR) {
+        pose_in_group = (int)(k / groups);
+        g = k - (int64_t)pose_in_group * groups;
+    } else {
+        g = k / poses_per_group;
+        pose_in_group = (int)(k - g * poses_per_group);
+    }
+    if (!WRITE && __ldcg(first + g) < pose_in_group) return;
+    const float *p = poses + 3 * k;
+    const float thw = __ldg(p + 2);
+    const rl::GridPose gp = rl::world_to_grid(P.w, __ldg(p), __ldg(p + 1), thw);
+    const float thg = __fadd_rn(-__fadd_rn(thw, fmaf((float)j, inc, -0.5f * fov)), P.w.rotation_const);
+    float s, c;
+    rl::glibc_sincosf(thg, &s, &c);
+    uint32_t steps = 0;
+    const float r = __fmul_rn(rl::march_ray<false>(P, gp.y, gp.x, c, s, steps), P.w.scale);
+    if (WRITE) outs[i] = r;
+    if (((double)r - __ldg(edge + j)) < thresh) atomicMin(first + g, pose_in_group);
+}
+
+// Car::setCarEdgeDistances on the host, with the host libm like the reference.
+void edge_distances(const CarParams &p, int num_rays, double min_ang, double inc, double scan_dist_to_base,
+                    std::vector<double> &edge)
+{
+    edge.assign(num_rays, 0.0);
+    const double side = p.width / 2.0;
+    const double front = p.wb - scan_dist_to_base;
+    const double back = scan_dist_to_base;
+    double a = min_ang;
+    for (int i = 0; i < num_rays; ++i) {
+        a += inc;   // incremented BEFORE use: edge[i] belongs to min_ang + (i+1)*inc
+        if (a > 0.0) {
+            if (a < REF_PI / 2.0) edge[i] = std::fmin(side / std::sin(a), front / std::cos(a));
+            else edge[i] = std::fmin(side / std::sin(a - REF_PI / 2.0), back / std::cos(a - REF_PI / 2.0));
+        } else {
+            if (a == 0.0) a += 0.0001;
+            if (a > -REF_PI / 2.0) edge[i] = std::fmin(side / std::sin(-a), front / std::cos(-a));
+            else edge[i] = std::fmin(side / std::sin(-a - REF_PI / 2.0), back / std::cos(-a - REF_PI / 2.0));
+        }
+    }
+}
+
+inline unsigned blocks_for(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+int32_t check_car(const rl_car *car, const char *who)
+{
+    if (!car) return rl::fail(RL_ERR_BAD_ARG, std::string(who) + ": null car");
+    if (car->num_rays <= 0 || !car->d_edge)
+        return rl::fail(RL_ERR_BAD_ARG, std::string(who) + ": call rl_car_set_edge_distances first");
+    return RL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+RL_API int32_t rl_car_create(const double *params17, int32_t device, rl_car **out)
+{
+    if (!params17 || !out) return rl::fail(RL_ERR_BAD_ARG, "rl_car_create: null pointer");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return rl::fail(RL_ERR_NO_DEVICE, "rl_car_create: no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return rl::fail(RL_ERR_NO_DEVICE, "rl_car_create: bad device index");
+    rl_car *c = new (std::nothrow) rl_car();
+    if (!c) return rl::fail(RL_ERR_OOM, "rl_car_create: host allocation failed");
+    const double *q = params17;
+    c->p = CarParams{q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8], q[9], q[10], q[11], q[12], q[13], q[14], q[15], q[16]};
+    c->device = device;
+    *out = c;
+    return RL_OK;
+}
+
+RL_API int32_t rl_car_destroy(rl_car *car)
+{
+    if (!car) return rl::fail(RL_ERR_BAD_ARG, "rl_car_destroy: null car");
+    {
+        rl::DeviceGuard guard(car->device);
+        cudaFree(car->d_edge);
+        cudaFree(car->d_first);
+    }
+    delete car;
+    return RL_OK;
+}
+
+RL_API int32_t rl_car_set_edge_distances(rl_car *car, int32_t num_rays, double min_ang, double ang_inc,
+                                         double scan_dist_to_base)
+{
+    if (!car || num_rays <= 0) return rl::fail(RL_ERR_BAD_ARG, "rl_car_set_edge_distances: bad argument");
+    rl::DeviceGuard guard(car->device);
+    edge_distances(car->p, num_rays, min_ang, ang_inc, scan_dist_to_base, car->edge);
+    cudaFree(car->d_edge);
+    car->d_edge = nullptr;
+    car->num_rays = 0;
+    RL_CUDA(cudaMalloc(&car->d_edge, (size_t)num_rays * sizeof(double)));
+    RL_CUDA(cudaMemcpy(car->d_edge, car->edge.data(), (size_t)num_rays * sizeof(double), cudaMemcpyHostToDevice));
+    car->num_rays = num_rays;
+    return RL_OK;
+}
+
+RL_API int32_t rl_car_get_edge_distances(const rl_car *car, double *out, int32_t num_rays)
+{
+    if (!car || !out || num_rays != car->num_rays) return rl::fail(RL_ERR_BAD_ARG, "rl_car_get_edge_distances: bad argument");
+    for (int i = 0; i < num_rays; ++i) out[i] = car->edge[i];
+    return RL_OK;
+}
+
+// Batched control() + updatePosition(dt): d_states (n,11) fp64 in place, per-car targets.
+RL_API int32_t rl_car_step(rl_car *car, double *d_states, const double *d_speed, const double *d_steer,
+                           int64_t n_cars, double dt, void *stream)
+{
+    if (!car || n_cars < 0 || (n_cars > 0 && (!d_states || !d_speed || !d_steer)))
+        return rl::fail(RL_ERR_BAD_ARG, "rl_car_step: bad argument");
+    if (n_cars == 0) return RL_OK;
+    rl::DeviceGuard guard(car->device);
+    car_step_kernel<<<blocks_for(n_cars, 128), 128, 0, (cudaStream_t)stream>>>(car->p, d_states, d_speed, d_steer, n_cars, dt);
+    RL_CUDA(cudaGetLastError());
+    return RL_OK;
+}
+
+// Car::isCrashed over device ranges: d_first[g] = first crashed pose of group g or -(poses_per_group+1).
+RL_API int32_t rl_is_crashed(rl_car *car, const float *d_rays, int64_t groups, int32_t poses_per_group,
+                             int32_t *d_first, void *stream)
+{
+    int32_t rc = check_car(car, "rl_is_crashed");
+    if (rc != RL_OK) return rc;
+    if (groups < 0 || poses_per_group <= 0 || (groups > 0 && (!d_rays || !d_first)))
+        return rl::fail(RL_ERR_BAD_ARG, "rl_is_crashed: bad argument");
+    if (groups == 0) return RL_OK;
+    rl::DeviceGuard guard(car->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t total = groups * poses_per_group * car->num_rays;
+    fill_i32_kernel<<<blocks_for(groups, 256), 256, 0, s>>>(d_first, groups, NO_CRASH);
+    crash_from_rays_kernel<<<blocks_for(total, 256), 256, 0, s>>>(d_rays, car->d_edge, total, car->num_rays,
+                                                                 poses_per_group, car->p.crash_thresh, d_first);
+    finalize_first_kernel<<<blocks_for(groups, 256), 256, 0, s>>>(d_first, groups, poses_per_group, nullptr, nullptr);
+    RL_CUDA(cudaGetLastError());
+    return RL_OK;
+}
+
+// scanMany + isCrashed in one pass (RacecarSimulator.checkCollisionMany): d_poses (groups *
+// poses_per_group, 3) fp32; beams = the car's edge table length; d_ranges may be NULL, in which
+// case no range is ever written and poses after a group's first crash are skipped.
+RL_API int32_t rl_scan_crash(rl_marcher *m, rl_car *car, const float *d_poses, int64_t groups,
+                             int32_t poses_per_group, float fov, int32_t *d_first, float *d_ranges,
+                             void *stream)
+{
+    int32_t rc = check_car(car, "rl_scan_crash");
+    if (rc != RL_OK) return rc;
+    if (!m || groups < 0 || poses_per_group <= 0 || (groups > 0 && (!d_poses || !d_first)))
+        return rl::fail(RL_ERR_BAD_ARG, "rl_scan_crash: bad argument");
+    if (rl::marcher_device(m) != car->device) return rl::fail(RL_ERR_BAD_ARG, "rl_scan_crash: car and marcher are on different devices");
+    if (groups == 0) return RL_OK;
+    rl::DeviceGuard guard(car->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t total = groups * poses_per_group * car->num_rays;
+    if (blocks_for(total, 256) == 0 || (total + 255) / 256 > 0x7fffffffLL)
+        return rl::fail(RL_ERR_BAD_ARG, "rl_scan_crash: too many rays for one call");
+    fill_i32_kernel<<<blocks_for(groups, 256), 256, 0, s>>>(d_first, groups, NO_CRASH);
+    const rl::MarchParams &P = rl::marcher_params(m);
+    if (d_ranges)
+        march_crash_kernel<true, false><<<blocks_for(total, 256), 256, 0, s>>>(
+            P, d_poses, car->d_edge, total, car->num_rays, poses_per_group, groups, fov, fov / (float)car->num_rays, car->p.crash_thresh, d_first, d_ranges);
+    else
+        march_crash_kernel<false, false><<<blocks_for(total, 256), 256, 0, s>>>(
+            P, d_poses, car->d_edge, total, car->num_rays, poses_per_group, groups, fov, fov / (float)car->num_rays, car->p.crash_thresh, d_first, nullptr);
+    finalize_first_kernel<<<blocks_for(groups, 256), 256, 0, s>>>(d_first, groups, poses_per_group, nullptr, nullptr);
+    RL_CUDA(cudaGetLastError());
+    return RL_OK;
+}
+
+// MCTS.rollout for n_cars cars at once, nothing leaving the GPU: `steps` updatePosition(dt) per car
+// with a new (speed, steer) from d_actions (n_cars, ceil(steps/action_every), 2) every
+// action_every-th step, one fan scan per step from the base-link pose (lidar_pose = 0, what
+// scripts/mcts.py:228-231 records) or the lidar pose (lidar_pose = 1, Car::getScanPose), crash test
+// per scan.  Outputs: d_states updated in place; d_crash_index[c] = first crashed step or
+// -(steps+1); d_reward[c] = sum of post-step velocities before the crash (all steps if none).
+// d_poses (steps, n_cars, 3) fp32 -- step-major -- and d_vsum (n_cars, steps) fp64 are caller-provided
+// scratch that also serve as outputs (the scanned poses, the running velocity sums).
+RL_API int32_t rl_rollout(rl_marcher *m, rl_car *car, double *d_states, const double *d_actions,
+                          int64_t n_cars, int32_t steps, int32_t action_every, double dt,
+                          int32_t lidar_pose, double scan_dist_to_base, float fov,
+                          int32_t *d_crash_index, double *d_reward, float *d_poses, double *d_vsum,
+                          void *stream)
+{
+    int32_t rc = check_car(car, "rl_rollout");
+    if (rc != RL_OK) return rc;
+    if (!m || n_cars < 0 || steps <= 0 || action_every <= 0 ||
+        (n_cars > 0 && (!d_states || !d_actions || !d_crash_index || !d_poses || !d_vsum)))
+        return rl::fail(RL_ERR_BAD_ARG, "rl_rollout: bad argument");
+    if (rl::marcher_device(m) != car->device) return rl::fail(RL_ERR_BAD_ARG, "rl_rollout: car and marcher are on different devices");
+    if (n_cars == 0) return RL_OK;
+    rl::DeviceGuard guard(car->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t total = n_cars * steps * car->num_rays;
+    if ((total + 255) / 256 > 0x7fffffffLL) return rl::fail(RL_ERR_BAD_ARG, "rl_rollout: too many rays for one call");
+    car_rollout_kernel<<<blocks_for(n_cars, 128), 128, 0, s>>>(car->p, d_states, d_actions, n_cars, steps, action_every, dt,
+                                                              lidar_pose, scan_dist_to_base, d_poses, d_vsum);
+    fill_i32_kernel<<<blocks_for(n_cars, 256), 256, 0, s>>>(d_crash_index, n_cars, NO_CRASH);
+    march_crash_kernel<false, true><<<blocks_for(total, 256), 256, 0, s>>>(
+        rl::marcher_params(m), d_poses, car->d_edge, total, car->num_rays, steps, n_cars, fov, fov / (float)car->num_rays,
+        car->p.crash_thresh, d_crash_index, nullptr);
+    finalize_first_kernel<<<blocks_for(n_cars, 256), 256, 0, s>>>(d_crash_index, n_cars, steps, d_vsum, d_reward);
+    RL_CUDA(cudaGetLastError());
+    return RL_OK;
+}
+
+}  // extern "C"

@@ -31,7 +31,7 @@ constexpr double PI63 = 0x1.921FB54442D18p-62;     // pi / 2^64
 }  // namespace trig
 
 // 4/pi to 192 bits, 8 new bits per entry (sincosf_data.c: __inv_pio4)
-__device__ __constant__ uint32_t g_inv_pio4[24] = {
+static __device__ __constant__ uint32_t g_inv_pio4[24] = {
     0xa2,       0xa2f9,     0xa2f983,   0xa2f9836e, 0xf9836e4e, 0x836e4e44, 0x6e4e4415, 0x4e441529,
     0x441529fc, 0x1529fc27, 0x29fc2757, 0xfc2757d1, 0x2757d1f5, 0x57d1f534, 0xd1f534dd, 0xf534ddc0,
     0x34ddc0db, 0xddc0db62, 0xc0db6295, 0xdb629599, 0x6295993c, 0x95993c43, 0x993c4390, 0x3c439041};
@@ -56,7 +56,7 @@ __device__ __forceinline__ double trig_cos_poly(double x2)
 }
 
 // reduce_large: |y| >= 120 (finite).  Returns the reduced argument, quadrant in n.
-__device__ __noinline__ double trig_reduce_large(uint32_t xi, int &n_out)
+static __device__ __noinline__ double trig_reduce_large(uint32_t xi, int &n_out)
 {
     const uint32_t *arr = &g_inv_pio4[(xi >> 26) & 15];
     const int shift = (xi >> 23) & 7;

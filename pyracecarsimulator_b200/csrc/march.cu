@@ -13,7 +13,7 @@ namespace {
 using rl::GridPose;
 using rl::MarchParams;
 
-constexpr int WARPS_PER_CTA = 8;
+constexpr int WARPS_PER_CTA = 4;   // 128-thread CTAs measured best (tools/tune_march)
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
 
 template <bool COUNT>
@@ -42,37 +42,40 @@ march_many_kernel(MarchParams P, const float *__restrict__ ins, float *__restric
     flush_steps<COUNT>(steps, counter);
 }
 
-// ---- one warp per (pose, beam segment), lanes over beams ----
+// ---- one thread per ray over the flat (pose, beam) index space: lanes run over adjacent beams ----
+// Measured on B200 (tools/tune_march): this finest-grained mapping beats warp-per-pose, beam
+// segments per warp, persistent work queues and multi-ray-per-lane variants; the march is bound
+// by L2 sector throughput and the hardware CTA scheduler is the cheapest load balancer.
 // FAN:   beam j heads theta + fmaf(j, fov/num_beams, -fov/2)   (fork's 4-arg calc_range_many)
 // !FAN:  beam a heads theta + angles[a]                        (calc_range_repeat_angles)
-template <bool FAN, bool COUNT>
+template <bool FAN, bool COUNT, bool SMALL>
 __global__ void __launch_bounds__(CTA_THREADS)
 march_pose_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_stride_floats,
-                  const float *__restrict__ angles, float *__restrict__ outs, int64_t num_poses,
-                  int num_beams, int segs_per_pose, int seg_len, float fov,
-                  unsigned long long *counter)
+                  const float *__restrict__ angles, float *__restrict__ outs, int64_t num_rays_total,
+                  int num_beams, rl::FastDiv div, float fov, float inc, unsigned long long *counter)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (int64_t)blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
-    const int64_t k = warp / segs_per_pose;
+    const int64_t i = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
     uint32_t steps = 0;
-    if (k < num_poses) {
-        const int seg = (int)(warp - k * segs_per_pose);
-        const float *p = poses + k * pose_stride_floats;
-        const GridPose g = rl::world_to_grid(P.w, __ldg(p), __ldg(p + 1), __ldg(p + 2));
-        const float thw = __ldg(p + 2);
-        const float inc = fov / (float)num_beams;
-        const float half = -0.5f * fov;
-        const int j_end = min(num_beams, (seg + 1) * seg_len);
-        float *o = outs + k * num_beams;
-        for (int j = seg * seg_len + lane; j < j_end; j += 32) {
-            float thg;
-            if (FAN) thg = __fadd_rn(-__fadd_rn(thw, fmaf((float)j, inc, half)), P.w.rotation_const);
-            else thg = __fsub_rn(g.theta, __ldg(angles + j));
-            float s, c;
-            rl::glibc_sincosf(thg, &s, &c);
-            o[j] = __fmul_rn(rl::march_ray<COUNT>(P, g.y, g.x, c, s, steps), P.w.scale);
+    if (i < num_rays_total) {
+        int64_t k;
+        int j;
+        if (SMALL) {   // fewer than 2^31 rays and at least 2 beams: multiply-high instead of a divide
+            const uint32_t k32 = rl::fast_div((uint32_t)i, div);
+            k = k32;
+            j = (int)((uint32_t)i - k32 * (uint32_t)num_beams);
+        } else {
+            k = i / num_beams;
+            j = (int)(i - k * num_beams);
         }
+        const float *p = poses + k * pose_stride_floats;
+        const float thw = __ldg(p + 2);
+        const GridPose g = rl::world_to_grid(P.w, __ldg(p), __ldg(p + 1), thw);
+        float thg;
+        if (FAN) thg = __fadd_rn(-__fadd_rn(thw, fmaf((float)j, inc, -0.5f * fov)), P.w.rotation_const);
+        else thg = __fsub_rn(g.theta, __ldg(angles + j));
+        float s, c;
+        rl::glibc_sincosf(thg, &s, &c);
+        outs[i] = __fmul_rn(rl::march_ray<COUNT>(P, g.y, g.x, c, s, steps), P.w.scale);
     }
     flush_steps<COUNT>(steps, counter);
 }
@@ -93,13 +96,18 @@ struct rl_marcher {
     int sm_count = 148;
     // host-variant staging (guarded by mu)
     std::mutex mu;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;   // double-buffered H2D -> march -> D2H pipeline
     float *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr, *d_angles = nullptr;
     size_t cap_in = 0, cap_out = 0, cap_angles = 0;  // floats
     // optional step counter
     bool count = false;
     unsigned long long *d_steps = nullptr;
 };
+
+namespace rl {
+const MarchParams &marcher_params(const rl_marcher *m) { return m->P; }
+int marcher_device(const rl_marcher *m) { return m->map->device; }
+}  // namespace rl
 
 namespace {
 
@@ -134,17 +142,16 @@ int32_t launch_many(rl_marcher *m, const float *d_ins, float *d_outs, int64_t n,
     return RL_OK;
 }
 
-// Split each pose's beams into segments so that small batches still fill the machine.
-void plan_segments(const rl_marcher *m, int64_t num_poses, int num_beams, int *segs, int *seg_len)
+rl::FastDiv make_fast_div(int d)
 {
-    const int groups = (num_beams + 31) / 32;               // 32-beam groups per pose
-    const int64_t want_warps = (int64_t)m->sm_count * 64 * 2;  // two full waves of resident warps
-    int64_t s = (want_warps + num_poses - 1) / num_poses;
-    if (s < 1) s = 1;
-    if (s > groups) s = groups;
-    int gl = (groups + (int)s - 1) / (int)s;                 // groups per segment
-    *seg_len = gl * 32;
-    *segs = (groups + gl - 1) / gl;
+    rl::FastDiv f{0, 0, (uint32_t)d};
+    if (d >= 2) {
+        int s = 1;
+        while ((1u << s) < (uint32_t)d) ++s;
+        f.magic = (uint32_t)((((uint64_t)1 << (31 + s)) + d - 1) / d);
+        f.shift = (uint32_t)(s - 1);
+    }
+    return f;
 }
 
 template <bool FAN>
@@ -152,32 +159,69 @@ int32_t launch_pose(rl_marcher *m, const float *d_poses, int64_t stride_rows, co
                     float *d_outs, int64_t num_poses, int num_beams, float fov, cudaStream_t s)
 {
     if (num_poses == 0 || num_beams == 0) return RL_OK;
-    int segs, seg_len;
-    plan_segments(m, num_poses, num_beams, &segs, &seg_len);
-    const int64_t warps = num_poses * segs;
-    const int64_t blocks = (warps + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    if (blocks > 0x7fffffffLL) return rl::fail(RL_ERR_BAD_ARG, "calc_range: too many poses for one call");
-    if (m->count)
-        march_pose_kernel<FAN, true><<<(unsigned)blocks, CTA_THREADS, 0, s>>>(
-            m->P, d_poses, stride_rows * 3, d_angles, d_outs, num_poses, num_beams, segs, seg_len, fov, m->d_steps);
-    else
-        march_pose_kernel<FAN, false><<<(unsigned)blocks, CTA_THREADS, 0, s>>>(
-            m->P, d_poses, stride_rows * 3, d_angles, d_outs, num_poses, num_beams, segs, seg_len, fov, nullptr);
+    const int64_t total = num_poses * num_beams;
+    const int64_t blocks = (total + CTA_THREADS - 1) / CTA_THREADS;
+    if (blocks > 0x7fffffffLL) return rl::fail(RL_ERR_BAD_ARG, "calc_range: too many rays for one call");
+    const rl::FastDiv div = make_fast_div(num_beams);
+    const float inc = fov / (float)num_beams;   // IEEE division, same bits as the oracle's
+    const bool small = num_beams >= 2 && total < ((int64_t)1 << 31);
+    unsigned long long *ctr = m->count ? m->d_steps : nullptr;
+#define RL_LAUNCH(COUNT, SMALL)                                                                    \
+    march_pose_kernel<FAN, COUNT, SMALL><<<(unsigned)blocks, CTA_THREADS, 0, s>>>(                   \
+        m->P, d_poses, stride_rows * 3, d_angles, d_outs, total, num_beams, div, fov, inc, ctr)
+    if (m->count) { if (small) RL_LAUNCH(true, true); else RL_LAUNCH(true, false); }
+    else { if (small) RL_LAUNCH(false, true); else RL_LAUNCH(false, false); }
+#undef RL_LAUNCH
     RL_CUDA(cudaGetLastError());
     return RL_OK;
 }
 
-// D2H of `n` floats into user memory: direct DMA when the user's buffer is pinned, else through
-// the marcher's pinned staging buffer.
-int32_t fetch(rl_marcher *m, float *outs, size_t n)
+// Host-pointer calls run as a software pipeline over sub-chunks on two streams: while one
+// sub-chunk's ranges travel device->host its successor is already marching (and, for the
+// row-per-ray form, its inputs are travelling host->device on the other copy engine).
+// `units` are poses (fan / repeat_angles) or rays (many); every unit has `in_floats` input and
+// `out_floats` output floats.  `launch(first_unit, count, d_in, d_out, stream)` enqueues the kernel.
+template <typename Launch>
+int32_t host_pipeline(rl_marcher *m, const float *ins, int64_t in_stride_floats, int in_floats,
+                      float *outs, int64_t units, int64_t out_floats, Launch launch)
 {
-    if (is_pinned(outs)) {
-        RL_CUDA(cudaMemcpyAsync(outs, m->d_out, n * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
-        RL_CUDA(cudaStreamSynchronize(m->stream));
-    } else {
-        RL_CUDA(cudaMemcpyAsync(m->h_out, m->d_out, n * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
-        RL_CUDA(cudaStreamSynchronize(m->stream));
-        std::memcpy(outs, m->h_out, n * sizeof(float));
+    if (units == 0 || out_floats == 0) return RL_OK;
+    int64_t big = (int64_t)(HOST_CHUNK_RAYS / (size_t)out_floats);   // units per staged chunk
+    if (big < 1) big = 1;
+    const bool in_pinned = in_stride_floats == in_floats && is_pinned(ins);
+    const bool out_pinned = is_pinned(outs);
+    cudaStream_t st[2] = {m->stream, m->stream2};
+    for (int64_t b = 0; b < units; b += big) {
+        const int64_t c = (units - b < big) ? units - b : big;
+        int32_t rc = ensure(&m->h_in, &m->d_in, &m->cap_in, (size_t)c * in_floats);
+        if (rc == RL_OK) rc = ensure(&m->h_out, &m->d_out, &m->cap_out, (size_t)c * out_floats);
+        if (rc != RL_OK) return rc;
+        const float *src = ins + b * in_stride_floats;
+        if (!in_pinned) {   // gather (strided fork layout) or stage (pageable) into pinned memory
+            if (in_stride_floats == in_floats) std::memcpy(m->h_in, src, (size_t)c * in_floats * sizeof(float));
+            else for (int64_t k = 0; k < c; ++k) std::memcpy(m->h_in + k * in_floats, src + k * in_stride_floats, in_floats * sizeof(float));
+            src = m->h_in;
+        }
+        float *dst = out_pinned ? outs + b * out_floats : m->h_out;
+        // sub-chunks of >= 256K ranges, at most 16 per chunk
+        int64_t nsub = (c * out_floats) >> 18;
+        nsub = nsub < 1 ? 1 : (nsub > 16 ? 16 : nsub);
+        if (nsub > c) nsub = c;
+        const int64_t per = (c + nsub - 1) / nsub;
+        int i = 0;
+        for (int64_t u = 0; u < c; u += per, ++i) {
+            const int64_t n = (c - u < per) ? c - u : per;
+            cudaStream_t s = st[i & 1];
+            RL_CUDA(cudaMemcpyAsync(m->d_in + u * in_floats, src + u * in_floats, (size_t)n * in_floats * sizeof(float),
+                                    cudaMemcpyHostToDevice, s));
+            rc = launch(u, n, m->d_in + u * in_floats, m->d_out + u * out_floats, s);
+            if (rc != RL_OK) return rc;
+            RL_CUDA(cudaMemcpyAsync(dst + u * out_floats, m->d_out + u * out_floats, (size_t)n * out_floats * sizeof(float),
+                                    cudaMemcpyDeviceToHost, s));
+        }
+        RL_CUDA(cudaStreamSynchronize(st[0]));
+        RL_CUDA(cudaStreamSynchronize(st[1]));
+        if (!out_pinned) std::memcpy(outs + b * out_floats, m->h_out, (size_t)c * out_floats * sizeof(float));
     }
     return RL_OK;
 }
@@ -215,6 +259,7 @@ int32_t rl_marcher_create(const rl_map *map, float max_range_px, uint32_t flags,
     m->P.w = map->world;
     cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, map->device);
     cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&m->d_steps, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(m->d_steps, 0, sizeof(unsigned long long));
     if (e != cudaSuccess) {
@@ -231,6 +276,7 @@ int32_t rl_marcher_destroy(rl_marcher *m)
     {
         rl::DeviceGuard guard(m->map->device);
         if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
+        if (m->stream2) { cudaStreamSynchronize(m->stream2); cudaStreamDestroy(m->stream2); }
         cudaFreeHost(m->h_in); cudaFreeHost(m->h_out);
         cudaFree(m->d_in); cudaFree(m->d_out); cudaFree(m->d_angles); cudaFree(m->d_steps);
     }
@@ -292,19 +338,10 @@ int32_t rl_calc_range_many_host(rl_marcher *m, const float *ins, float *outs, in
     if (!m || n < 0 || (n > 0 && (!ins || !outs))) return rl::fail(RL_ERR_BAD_ARG, "rl_calc_range_many_host: bad argument");
     rl::DeviceGuard guard(m->map->device);
     std::lock_guard<std::mutex> lock(m->mu);
-    for (int64_t b = 0; b < n; b += (int64_t)HOST_CHUNK_RAYS) {
-        const size_t c = (size_t)((n - b < (int64_t)HOST_CHUNK_RAYS) ? n - b : HOST_CHUNK_RAYS);
-        int32_t rc = ensure(&m->h_in, &m->d_in, &m->cap_in, 3 * c);
-        if (rc == RL_OK) rc = ensure(&m->h_out, &m->d_out, &m->cap_out, c);
-        if (rc != RL_OK) return rc;
-        const float *src = ins + 3 * b;
-        if (!is_pinned(src)) { std::memcpy(m->h_in, src, 3 * c * sizeof(float)); src = m->h_in; }
-        RL_CUDA(cudaMemcpyAsync(m->d_in, src, 3 * c * sizeof(float), cudaMemcpyHostToDevice, m->stream));
-        rc = launch_many(m, m->d_in, m->d_out, (int64_t)c, m->stream);
-        if (rc == RL_OK) rc = fetch(m, outs + b, c);
-        if (rc != RL_OK) return rc;
-    }
-    return RL_OK;
+    return host_pipeline(m, ins, 3, 3, outs, n, 1,
+                         [&](int64_t, int64_t cnt, const float *d_in, float *d_out, cudaStream_t s) {
+                             return launch_many(m, d_in, d_out, cnt, s);
+                         });
 }
 
 int32_t rl_calc_range_fan_host(rl_marcher *m, const float *poses, int64_t pose_stride_rows, float *outs,
@@ -314,22 +351,11 @@ int32_t rl_calc_range_fan_host(rl_marcher *m, const float *poses, int64_t pose_s
         return rl::fail(RL_ERR_BAD_ARG, "rl_calc_range_fan_host: bad argument");
     rl::DeviceGuard guard(m->map->device);
     std::lock_guard<std::mutex> lock(m->mu);
-    int64_t chunk = (int64_t)(HOST_CHUNK_RAYS / (size_t)num_rays);
-    if (chunk < 1) chunk = 1;
-    for (int64_t b = 0; b < num_poses; b += chunk) {
-        const int64_t c = (num_poses - b < chunk) ? num_poses - b : chunk;
-        int32_t rc = ensure(&m->h_in, &m->d_in, &m->cap_in, 3 * (size_t)c);
-        if (rc == RL_OK) rc = ensure(&m->h_out, &m->d_out, &m->cap_out, (size_t)c * num_rays);
-        if (rc != RL_OK) return rc;
-        // only row k*pose_stride_rows of each pose's block is meaningful: gather to a compact (c,3)
-        for (int64_t k = 0; k < c; ++k)
-            std::memcpy(m->h_in + 3 * k, poses + 3 * (b + k) * pose_stride_rows, 3 * sizeof(float));
-        RL_CUDA(cudaMemcpyAsync(m->d_in, m->h_in, 3 * (size_t)c * sizeof(float), cudaMemcpyHostToDevice, m->stream));
-        rc = launch_pose<true>(m, m->d_in, 1, nullptr, m->d_out, c, num_rays, fov, m->stream);
-        if (rc == RL_OK) rc = fetch(m, outs + b * num_rays, (size_t)c * num_rays);
-        if (rc != RL_OK) return rc;
-    }
-    return RL_OK;
+    // only row k*pose_stride_rows of each pose's block is meaningful: the pipeline gathers them
+    return host_pipeline(m, poses, 3 * pose_stride_rows, 3, outs, num_poses, num_rays,
+                         [&](int64_t, int64_t cnt, const float *d_in, float *d_out, cudaStream_t s) {
+                             return launch_pose<true>(m, d_in, 1, nullptr, d_out, cnt, num_rays, fov, s);
+                         });
 }
 
 int32_t rl_calc_range_repeat_angles_host(rl_marcher *m, const float *poses, const float *angles,
@@ -343,23 +369,11 @@ int32_t rl_calc_range_repeat_angles_host(rl_marcher *m, const float *poses, cons
     std::lock_guard<std::mutex> lock(m->mu);
     int32_t rc = ensure(nullptr, &m->d_angles, &m->cap_angles, (size_t)num_angles);
     if (rc != RL_OK) return rc;
-    RL_CUDA(cudaMemcpyAsync(m->d_angles, angles, (size_t)num_angles * sizeof(float), cudaMemcpyHostToDevice, m->stream));
-    RL_CUDA(cudaStreamSynchronize(m->stream));  // `angles` may be pageable and reused by the caller
-    int64_t chunk = (int64_t)(HOST_CHUNK_RAYS / (size_t)num_angles);
-    if (chunk < 1) chunk = 1;
-    for (int64_t b = 0; b < num_poses; b += chunk) {
-        const int64_t c = (num_poses - b < chunk) ? num_poses - b : chunk;
-        rc = ensure(&m->h_in, &m->d_in, &m->cap_in, 3 * (size_t)c);
-        if (rc == RL_OK) rc = ensure(&m->h_out, &m->d_out, &m->cap_out, (size_t)c * num_angles);
-        if (rc != RL_OK) return rc;
-        const float *src = poses + 3 * b;
-        if (!is_pinned(src)) { std::memcpy(m->h_in, src, 3 * (size_t)c * sizeof(float)); src = m->h_in; }
-        RL_CUDA(cudaMemcpyAsync(m->d_in, src, 3 * (size_t)c * sizeof(float), cudaMemcpyHostToDevice, m->stream));
-        rc = launch_pose<false>(m, m->d_in, 1, m->d_angles, m->d_out, c, num_angles, 0.0f, m->stream);
-        if (rc == RL_OK) rc = fetch(m, outs + b * num_angles, (size_t)c * num_angles);
-        if (rc != RL_OK) return rc;
-    }
-    return RL_OK;
+    RL_CUDA(cudaMemcpy(m->d_angles, angles, (size_t)num_angles * sizeof(float), cudaMemcpyHostToDevice));
+    return host_pipeline(m, poses, 3, 3, outs, num_poses, num_angles,
+                         [&](int64_t, int64_t cnt, const float *d_in, float *d_out, cudaStream_t s) {
+                             return launch_pose<false>(m, d_in, 1, m->d_angles, d_out, cnt, num_angles, 0.0f, s);
+                         });
 }
 
 }  // extern "C"

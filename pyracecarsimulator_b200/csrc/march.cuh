@@ -23,19 +23,21 @@ __device__ __forceinline__ GridPose world_to_grid(const WorldFrame &w, float xw,
 // Sphere-trace one ray in grid coordinates.  (x0, dx) run along the FIRST grid index (msg rows),
 // (y0, dy) along the second (msg columns) -- the caller has already applied upstream's
 // calc_range(y, x, theta) argument swap.  Returns pixels.  `steps` counts distance-field loads.
+//
+// Bounds: upstream tests the TRUNCATED integers (px < 0 || px >= width ...), so (-1, 0) is cell 0
+// and in bounds; cvt.rzi saturates, so +-inf and huge values leave the map like x86's cvttss2si
+// INT_MIN does.  Only NaN converts differently (0 here, INT_MIN on x86), hence the one check
+// before the loop: a NaN pose or heading leaves the map at once.
 template <bool COUNT>
 __device__ __forceinline__ float march_ray(const MarchParams &P, float x0, float y0, float dx,
                                            float dy, uint32_t &steps)
 {
+    if (!(x0 == x0) || !(y0 == y0) || !(dx == dx) || !(dy == dy)) return P.max_range;
     float t = 0.0f;
     while (t < P.max_range) {
-        const float fx = fmaf(dx, t, x0);
-        const float fy = fmaf(dy, t, y0);
-        // (int) truncates toward zero, so (-1, 0) is cell 0 and in bounds; NaN fails every
-        // comparison and leaves the map like x86's cvttss2si INT_MIN does upstream.
-        if (!(fx > -1.0f && fx < P.frows && fy > -1.0f && fy < P.fcols)) return P.max_range;
-        const int px = __float2int_rz(fx);
-        const int py = __float2int_rz(fy);
+        const int px = __float2int_rz(fmaf(dx, t, x0));
+        const int py = __float2int_rz(fmaf(dy, t, y0));
+        if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) return P.max_range;
         const float d = __ldg(P.dist + (px * P.cols + py));
         if (COUNT) ++steps;
         if (d <= 0.0f) {
@@ -47,5 +49,13 @@ __device__ __forceinline__ float march_ray(const MarchParams &P, float x0, float
     }
     return P.max_range;
 }
+
+// Unsigned division by a launch-constant divisor d >= 2, exact for numerators below 2^31:
+// n / d == umulhi(n, magic) >> shift with s = ceil(log2 d), magic = ceil(2^(31+s) / d), shift = s-1.
+struct FastDiv {
+    uint32_t magic, shift, d;
+};
+
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv &f) { return __umulhi(n, f.magic) >> f.shift; }
 
 }  // namespace rl

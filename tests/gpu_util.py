@@ -17,8 +17,10 @@ def build_synth(orc, n, seed, tmp_path_factory=None):
     return omap, y, occ, dist
 
 
-def assert_ranges_match(got, want, resolution, min_identical=0.999):
-    """north_star: all within max(1e-4 rel, 0.5 cell); >= 99.9 % of beams bit-identical."""
+def assert_ranges_match(got, want, resolution, min_identical=1.0):
+    """north_star bar: all within max(1e-4 rel, 0.5 cell) and >= 99.9 % of beams bit-identical.
+    The device evaluates glibc's sinf/cosf (csrc/glibc_trig.cuh) and the march is IEEE-exact
+    fp32 in the oracle's order, so the tests ask for more: every beam bit-identical."""
     got = np.asarray(got)
     want = np.asarray(want)
     assert got.shape == want.shape

@@ -1,0 +1,187 @@
+"""Vehicle model, crash test and fused rollout on the GPU (csrc/car.cu) against the oracle
+(oracle/car_oracle.c, itself bit-exact against the unmodified reference Car) and the golden
+vectors produced by the reference Car.
+
+Tolerances: the crash test and edge distances are exact.  The fp64 dynamics use CUDA's
+cos/sin/tan, which may differ from the host libm in the last ulp, so states are compared to
+1e-11 relative (+1e-13 absolute) after up to 200 steps; poses narrowed to fp32 must then be
+identical for >= 99.99 % of entries and crash indices for >= 99.9 % of cars."""
+import numpy as np
+import pytest
+
+from pyracecarsimulator_b200 import maps, range_libc
+from pyracecarsimulator_b200.racecar import BatchedCar, car_params
+
+pytestmark = pytest.mark.gpu
+
+FOV, NRAYS, DIST_TO_BASE = 4.71, 1080, 0.275
+
+
+@pytest.fixture(scope="module")
+def car():
+    c = BatchedCar()
+    c.setCarEdgeDistances(NRAYS, -FOV / 2.0, FOV / NRAYS, DIST_TO_BASE)
+    return c
+
+
+@pytest.fixture(scope="module")
+def col(orc, colombia, colombia_scan):
+    binar = np.where(colombia_scan["grid"] > 0, 255, 0).ravel()
+    omap = range_libc.PyOMap(maps.OccupancyGrid.make(binar, 435, 350, colombia["resolution"], colombia["origin"]))
+    dist = orc.edt_float(colombia_scan["occ"])
+    return dict(rm=range_libc.PyRayMarchingGPU(omap, 300), orc=orc.Marcher(dist, 300, colombia["resolution"], colombia["origin"]),
+                dist=dist, res=colombia["resolution"], origin=colombia["origin"])
+
+
+def close_states(a, b):
+    return np.allclose(a, b, rtol=1e-11, atol=1e-13)
+
+
+def test_params_follow_the_reference_constructor_order(orc):
+    assert np.array_equal(car_params(), orc.car_params().as_array())
+
+
+def test_edge_distances_exact(orc, car, car_golden):
+    want = orc.car_edge_distances(orc.car_params(), NRAYS, -FOV / 2.0, FOV / NRAYS, DIST_TO_BASE)
+    assert np.array_equal(car.edge_distances(), want)
+    # and consistent with the reference's own isCrashed boundary (golden, from the real Car)
+    safe = car_golden["first_safe_ray"]
+    assert np.all(safe.astype(np.float64) - want >= 0.001)
+
+
+def test_step_matches_golden_reference_trajectories(car, car_golden):
+    import torch
+    g = car_golden
+    n, steps = g["init"].shape[0], g["states"].shape[1]
+    st = torch.from_numpy(g["init"].copy()).cuda()
+    for i in range(steps):
+        a = torch.from_numpy(np.ascontiguousarray(g["actions"][:, i // 10])).cuda()
+        car.step(st, a[:, 0].contiguous(), a[:, 1].contiguous(), 0.01)
+        assert close_states(st.cpu().numpy(), g["states"][:, i]), i
+    pose = BatchedCar.scan_pose(st, DIST_TO_BASE).cpu().numpy()
+    assert np.allclose(pose, g["scan_poses"][:, -1], rtol=1e-11, atol=1e-13)
+
+
+def test_step_random_states_vs_oracle(orc, car):
+    import torch
+    rng = np.random.default_rng(1)
+    n = 5000
+    s0 = np.zeros((n, 11))
+    s0[:, :2] = rng.uniform(-5, 5, (n, 2))
+    s0[:, 2] = rng.uniform(-np.pi, np.pi, n)
+    s0[:, 3] = rng.uniform(-1, 7.5, n)
+    s0[:, 4] = rng.uniform(-0.45, 0.45, n)
+    s0[:, 5] = rng.uniform(-1, 1, n)
+    s0[:, 6] = rng.uniform(-0.2, 0.2, n)
+    s0[:, 7] = rng.integers(0, 2, n)
+    speed, steer = rng.uniform(0, 7, n), rng.uniform(-0.4189, 0.4189, n)
+    st = torch.from_numpy(s0.copy()).cuda()
+    car.step(st, torch.from_numpy(speed).cuda(), torch.from_numpy(steer).cuda(), 0.01)
+    p = orc.car_params()
+    want = s0.copy()
+    for i in range(n):
+        orc.car_step(p, want[i], speed[i], steer[i], 0.01)
+    got = st.cpu().numpy()
+    assert close_states(got, want)
+    assert np.array_equal(got[:, 7], want[:, 7]) and np.array_equal(got[:, 10], want[:, 10])
+
+
+def test_is_crashed_exact_boundary(orc, car, car_golden):
+    import torch
+    edge = car.edge_distances()
+    rng = np.random.default_rng(2)
+    groups, per = 40, 6
+    rays = rng.uniform(0.3, 10.0, (groups, per, NRAYS)).astype(np.float32)
+    safe = car_golden["first_safe_ray"]
+    for g in range(groups):                     # plant exact-boundary values from the reference
+        k, j = rng.integers(per), rng.integers(NRAYS)
+        rays[g, k, j] = safe[j] if g % 2 else np.nextafter(safe[j], np.float32(-1))
+    rays[3] = 5.0
+    got = car.is_crashed_many(torch.from_numpy(rays).cuda().reshape(-1), groups, per).cpu().numpy()
+    want = np.array([orc.car_is_crashed(rays[g].ravel(), edge, NRAYS, per, 0.001) for g in range(groups)])
+    assert np.array_equal(got, want)
+    assert got[3] == -(per + 1)
+    # upstream signature
+    assert car.isCrashed(rays[5].ravel(), NRAYS, per) == want[5]
+    clear = np.full(3 * NRAYS, 5.0, np.float32)
+    assert car.isCrashed(clear, NRAYS, 3) == -4
+    clear[NRAYS + 500] = 0.05
+    assert car.isCrashed(clear, NRAYS, 3) == 1
+
+
+def test_scan_crash_matches_scan_then_is_crashed(orc, car, col):
+    import torch
+    edge = car.edge_distances()
+    rng = np.random.default_rng(3)
+    groups, per = 24, 10
+    poses = maps.sample_free_poses(col["dist"], groups * per, 77, col["res"], col["origin"], min_clear_px=1.0)
+    want_ranges = col["orc"].calc_range_fan(poses, NRAYS, FOV)
+    want = np.array([orc.car_is_crashed(want_ranges[g * per * NRAYS:(g + 1) * per * NRAYS], edge, NRAYS, per, 0.001)
+                     for g in range(groups)])
+    assert (want >= 0).any() and (want < 0).any()
+    dp = torch.from_numpy(poses).cuda()
+    first, ranges = car.scan_crash(col["rm"], dp, groups, per, FOV, want_ranges=True)
+    assert np.array_equal(ranges.cpu().numpy(), want_ranges)
+    assert np.array_equal(first.cpu().numpy(), want)
+    first2, none = car.scan_crash(col["rm"], dp, groups, per, FOV, want_ranges=False)
+    assert none is None and np.array_equal(first2.cpu().numpy(), want)
+
+
+def oracle_rollout(orc, marcher, edge, s0, actions, steps, lidar_pose):
+    p = orc.car_params()
+    st = s0.copy()
+    poses = np.zeros((steps, 3), np.float32)
+    v = np.zeros(steps)
+    for i in range(steps):
+        sp, sa = actions[i // 10]
+        orc.car_step(p, st, sp, sa, 0.01)
+        src = orc.car_scan_pose(st, DIST_TO_BASE) if lidar_pose else st[:3]
+        poses[i] = src            # f64 -> f32, where the reference narrows (scripts/mcts.py:229-231)
+        v[i] = st[3]
+    ranges = marcher.calc_range_fan(poses, NRAYS, FOV)
+    idx = orc.car_is_crashed(ranges, edge, NRAYS, steps, 0.001)
+    reward = v.sum() if idx < 0 else v[:idx].sum()
+    return st, poses, idx, reward
+
+
+@pytest.mark.parametrize("lidar_pose", [False, True])
+def test_fused_rollout_vs_oracle(orc, car, col, lidar_pose):
+    import torch
+    rng = np.random.default_rng(4)
+    n, steps = 96, 50
+    start = maps.sample_free_poses(col["dist"], n, 99, col["res"], col["origin"], min_clear_px=6.0)
+    s0 = np.zeros((n, 11))
+    s0[:, :3] = start
+    s0[:, 3] = 2.0
+    actions = np.stack([rng.uniform(0, 7.0, (n, 5)), rng.uniform(-0.4189, 0.4189, (n, 5))], axis=2)
+    st = torch.from_numpy(s0.copy()).cuda()
+    out = car.rollout(col["rm"], st, torch.from_numpy(actions).cuda(), steps, FOV, lidar_pose=lidar_pose,
+                      scan_dist_to_base=DIST_TO_BASE)
+    edge = car.edge_distances()
+    got_idx, got_rew = out["crash_index"].cpu().numpy(), out["reward"].cpu().numpy()
+    got_poses = out["poses"].cpu().numpy()          # (steps, n, 3), step-major
+    same_idx, same_pose = 0, 0
+    for c in range(n):
+        w_st, w_poses, w_idx, w_rew = oracle_rollout(orc, col["orc"], edge, s0[c], actions[c], steps, lidar_pose)
+        assert close_states(st[c].cpu().numpy(), w_st), c
+        same_pose += int((got_poses[:, c] == w_poses).sum())
+        if got_idx[c] == w_idx:
+            same_idx += 1
+            assert got_rew[c] == pytest.approx(w_rew, rel=1e-11, abs=1e-12)
+    assert same_pose >= 0.9999 * n * steps * 3
+    assert same_idx >= 0.999 * n
+    assert (got_idx >= 0).any() and (got_idx < 0).any()     # the case exercises both outcomes
+    assert np.all(got_idx[got_idx < 0] == -(steps + 1))
+
+
+def test_argument_errors(car, col):
+    import torch
+    fresh = BatchedCar()
+    with pytest.raises(ValueError):          # edge distances not set yet
+        fresh.is_crashed_many(torch.zeros(NRAYS, dtype=torch.float32, device="cuda"), 1, 1)
+    with pytest.raises(ValueError):
+        car.step(torch.zeros((4, 10), dtype=torch.float64, device="cuda"), torch.zeros(4, dtype=torch.float64, device="cuda"),
+                 torch.zeros(4, dtype=torch.float64, device="cuda"))
+    with pytest.raises(ValueError):
+        car.rollout(col["rm"], torch.zeros((4, 11), dtype=torch.float64, device="cuda"),
+                    torch.zeros((4, 3, 2), dtype=torch.float64, device="cuda"), 50, FOV)

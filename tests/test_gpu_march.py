@@ -101,8 +101,7 @@ def test_fan_ragged_beam_counts(col, num_rays):
     poses = maps.sample_free_poses(col["dist"], 37, num_rays, col["res"], col["origin"])
     out = np.full(37 * num_rays + 5, -1.0, np.float32)
     col["rm"].calc_range_fan(poses, out[:37 * num_rays], FOV, num_rays)
-    assert_ranges_match(out[:37 * num_rays], col["orc"].calc_range_fan(poses, num_rays, FOV), col["res"],
-                        min_identical=0.995 if num_rays < 100 else 0.999)
+    assert_ranges_match(out[:37 * num_rays], col["orc"].calc_range_fan(poses, num_rays, FOV), col["res"])
     assert np.all(out[37 * num_rays:] == -1.0)   # nothing written past the end
 
 
@@ -229,4 +228,4 @@ def test_rotated_origin_map(orc):
                      rng.uniform(-np.pi, np.pi, 400)], axis=1).astype(np.float32)
     out = np.zeros(400, np.float32)
     rm.calc_range_many(rays, out)
-    assert_ranges_match(out, m.calc_range_many(rays), 0.1, min_identical=0.99)
+    assert_ranges_match(out, m.calc_range_many(rays), 0.1)

@@ -1,0 +1,667 @@
+// tools/tune_march.cu -- development harness (not shipped, not on the product path): times
+// candidate fan-march kernel structures on the same distance field and poses, checks every
+// candidate bit-for-bit against the straightforward one, and prints a table.
+//   python tools/tune_prep.py /tmp/tune && tools/tune_march /tmp/tune [reps]
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../pyracecarsimulator_b200/csrc/glibc_trig.cuh"
+#include "../pyracecarsimulator_b200/csrc/march.cuh"
+
+using rl::GridPose;
+using rl::MarchParams;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1);} } while (0)
+
+struct Args {
+    MarchParams P;
+    const float *poses;
+    float *outs;
+    int num_poses, num_beams;
+    float fov;
+    unsigned int *counter;   // work queue
+};
+
+__device__ __forceinline__ float beam_heading(const Args &a, float thw, int j)
+{
+    const float inc = a.fov / (float)a.num_beams;
+    return __fadd_rn(-__fadd_rn(thw, fmaf((float)j, inc, -0.5f * a.fov)), a.P.w.rotation_const);
+}
+
+// ---------------------------------------------------------------- V0: product structure
+template <int WPC>
+__global__ void __launch_bounds__(WPC * 32) k_base(Args a, int segs, int seg_len)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * WPC + (threadIdx.x >> 5);
+    const int k = warp / segs;
+    if (k >= a.num_poses) return;
+    const int seg = warp - k * segs;
+    const float *p = a.poses + 3 * k;
+    const GridPose g = rl::world_to_grid(a.P.w, __ldg(p), __ldg(p + 1), __ldg(p + 2));
+    const float thw = __ldg(p + 2);
+    const int j_end = min(a.num_beams, (seg + 1) * seg_len);
+    float *o = a.outs + (size_t)k * a.num_beams;
+    uint32_t st = 0;
+    for (int j = seg * seg_len + lane; j < j_end; j += 32) {
+        float s, c;
+        rl::glibc_sincosf(beam_heading(a, thw, j), &s, &c);
+        o[j] = __fmul_rn(rl::march_ray<false>(a.P, g.y, g.x, c, s, st), a.P.w.scale);
+    }
+}
+
+// ---------------------------------------------------------------- V1: persistent warps, global queue of
+// (pose, chunk) tasks, ILP independent rays per lane marched in lockstep
+template <int ILP>
+__device__ __forceinline__ void march_ilp(const MarchParams &P, float x0, float y0, const float (&dx)[ILP],
+                                          const float (&dy)[ILP], bool (&live)[ILP], float (&res)[ILP])
+{
+    float t[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) { t[i] = 0.f; res[i] = P.max_range; }
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) any |= live[i];
+    while (any) {
+        float d[ILP];
+        int px[ILP], py[ILP];
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) {
+            d[i] = 1.0f;
+            if (live[i]) {
+                const float fx = fmaf(dx[i], t[i], x0);
+                const float fy = fmaf(dy[i], t[i], y0);
+                if (!(fx > -1.0f && fx < P.frows && fy > -1.0f && fy < P.fcols)) { live[i] = false; }
+                else {
+                    px[i] = __float2int_rz(fx);
+                    py[i] = __float2int_rz(fy);
+                    d[i] = __ldg(P.dist + (px[i] * P.cols + py[i]));
+                }
+            }
+        }
+        any = false;
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) {
+            if (live[i]) {
+                if (d[i] <= 0.0f) {
+                    const float xd = __fsub_rn((float)px[i], x0);
+                    const float yd = __fsub_rn((float)py[i], y0);
+                    res[i] = sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+                    live[i] = false;
+                } else {
+                    t[i] = __fadd_rn(t[i], fmaxf(__fmul_rn(d[i], 0.999f), 1.0f));
+                    if (!(t[i] < P.max_range)) live[i] = false;
+                }
+            }
+            any |= live[i];
+        }
+    }
+}
+
+template <int ILP, int WPC>
+__global__ void __launch_bounds__(WPC * 32) k_persist(Args a, int chunks_per_pose)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned total = (unsigned)a.num_poses * chunks_per_pose;
+    unsigned task = 0;
+    if (lane == 0) task = atomicAdd(a.counter, 1u);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    while (task < total) {
+        unsigned next = 0;
+        if (lane == 0) next = atomicAdd(a.counter, 1u);   // prefetch the next task id
+        const int k = task / chunks_per_pose;
+        const int chunk = task - k * chunks_per_pose;
+        const float *p = a.poses + 3 * k;
+        const GridPose g = rl::world_to_grid(a.P.w, __ldg(p), __ldg(p + 1), __ldg(p + 2));
+        const float thw = __ldg(p + 2);
+        float dx[ILP], dy[ILP], res[ILP];
+        bool live[ILP];
+        const int j0 = chunk * 32 * ILP + lane;
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) {
+            const int j = j0 + 32 * i;
+            live[i] = j < a.num_beams;
+            rl::glibc_sincosf(beam_heading(a, thw, j), &dy[i], &dx[i]);
+        }
+        march_ilp<ILP>(a.P, g.y, g.x, dx, dy, live, res);
+        float *o = a.outs + (size_t)k * a.num_beams;
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) {
+            const int j = j0 + 32 * i;
+            if (j < a.num_beams) o[j] = __fmul_rn(res[i], a.P.w.scale);
+        }
+        task = __shfl_sync(0xffffffffu, next, 0);
+    }
+}
+
+// ---------------------------------------------------------------- V2: persistent warps, NB beams per lane with
+// directions precomputed in registers, per-lane "flattened" loop (a lane starts its next beam as
+// soon as its current one ends, without waiting for the other lanes)
+template <int NB, int WPC>
+__global__ void __launch_bounds__(WPC * 32) k_flat(Args a, int chunks_per_pose)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned total = (unsigned)a.num_poses * chunks_per_pose;
+    const MarchParams &P = a.P;
+    unsigned task = 0;
+    if (lane == 0) task = atomicAdd(a.counter, 1u);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    while (task < total) {
+        unsigned next = 0;
+        if (lane == 0) next = atomicAdd(a.counter, 1u);
+        const int k = task / chunks_per_pose;
+        const int chunk = task - k * chunks_per_pose;
+        const float *p = a.poses + 3 * k;
+        const GridPose g = rl::world_to_grid(P.w, __ldg(p), __ldg(p + 1), __ldg(p + 2));
+        const float thw = __ldg(p + 2);
+        const float x0 = g.y, y0 = g.x;
+        float dxs[NB], dys[NB];
+        const int j0 = chunk * 32 * NB + lane;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) rl::glibc_sincosf(beam_heading(a, thw, j0 + 32 * i), &dys[i], &dxs[i]);
+        float *o = a.outs + (size_t)k * a.num_beams;
+        int b = 0;
+        int nb = 0;   // beams this lane owns in this chunk
+#pragma unroll
+        for (int i = 0; i < NB; ++i) nb += (j0 + 32 * i < a.num_beams) ? 1 : 0;
+        float dx = dxs[0], dy = dys[0], t = 0.f;
+        while (b < nb) {
+            const float fx = fmaf(dx, t, x0);
+            const float fy = fmaf(dy, t, y0);
+            float r = P.max_range;
+            bool done = false;
+            if (!(fx > -1.0f && fx < P.frows && fy > -1.0f && fy < P.fcols)) done = true;
+            else {
+                const int px = __float2int_rz(fx), py = __float2int_rz(fy);
+                const float d = __ldg(P.dist + (px * P.cols + py));
+                if (d <= 0.0f) {
+                    const float xd = __fsub_rn((float)px, x0), yd = __fsub_rn((float)py, y0);
+                    r = sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+                    done = true;
+                } else {
+                    t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+                    done = !(t < P.max_range);
+                }
+            }
+            if (done) {
+                o[j0 + 32 * b] = __fmul_rn(r, P.w.scale);
+                ++b;
+                t = 0.f;
+#pragma unroll
+                for (int i = 1; i < NB; ++i)
+                    if (b == i) { dx = dxs[i]; dy = dys[i]; }
+            }
+        }
+        task = __shfl_sync(0xffffffffu, next, 0);
+    }
+}
+
+// ---------------------------------------------------------------- V3: one CTA per pose (all its rays on one SM, so
+// the near field of the pose is fetched into that SM's L1 once); warps pull 32*ILP-beam chunks
+// from a shared-memory counter; CTAs pull poses from the global counter
+template <int ILP, int WPC>
+__global__ void __launch_bounds__(WPC * 32) k_cta_pose(Args a, int chunks_per_pose)
+{
+    __shared__ int s_pose, s_chunk;
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        if (threadIdx.x == 0) { s_pose = (int)atomicAdd(a.counter, 1u); s_chunk = 0; }
+        __syncthreads();
+        const int k = s_pose;
+        if (k >= a.num_poses) break;
+        const float *p = a.poses + 3 * k;
+        const GridPose g = rl::world_to_grid(a.P.w, __ldg(p), __ldg(p + 1), __ldg(p + 2));
+        const float thw = __ldg(p + 2);
+        float *o = a.outs + (size_t)k * a.num_beams;
+        for (;;) {
+            int chunk = 0;
+            if (lane == 0) chunk = atomicAdd(&s_chunk, 1);
+            chunk = __shfl_sync(0xffffffffu, chunk, 0);
+            if (chunk >= chunks_per_pose) break;
+            float dx[ILP], dy[ILP], res[ILP];
+            bool live[ILP];
+            const int j0 = chunk * 32 * ILP + lane;
+#pragma unroll
+            for (int i = 0; i < ILP; ++i) {
+                const int j = j0 + 32 * i;
+                live[i] = j < a.num_beams;
+                rl::glibc_sincosf(beam_heading(a, thw, j), &dy[i], &dx[i]);
+            }
+            march_ilp<ILP>(a.P, g.y, g.x, dx, dy, live, res);
+#pragma unroll
+            for (int i = 0; i < ILP; ++i) {
+                const int j = j0 + 32 * i;
+                if (j < a.num_beams) o[j] = __fmul_rn(res[i], a.P.w.scale);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- V4: flat thread-per-ray with alternative
+// distance-field layouts (the march is bound by L2 sector requests: make sectors 2-D)
+enum Layout { ROWMAJOR = 0, TILE_2x4 = 1, TILE_LINE = 2, TEX = 3, U16_4x4 = 4, TILE_4x2 = 5 };
+
+struct LayoutArgs {
+    const float *tiled;      // re-laid-out copy
+    const unsigned short *d2u16;
+    cudaTextureObject_t tex;
+    int tiles_per_row;       // in tiles along cols
+};
+
+template <int L>
+__device__ __forceinline__ float fetch(const MarchParams &P, const LayoutArgs &la, int px, int py)
+{
+    if (L == ROWMAJOR) return __ldg(P.dist + (px * P.cols + py));
+    if (L == TILE_2x4) {   // 32 B sector = 2 rows x 4 cols
+        const int idx = (((px >> 1) * la.tiles_per_row + (py >> 2)) << 3) | ((px & 1) << 2) | (py & 3);
+        return __ldg(la.tiled + idx);
+    }
+    if (L == TILE_4x2) {   // 32 B sector = 4 rows x 2 cols
+        const int idx = (((px >> 2) * la.tiles_per_row + (py >> 1)) << 3) | ((px & 3) << 1) | (py & 1);
+        return __ldg(la.tiled + idx);
+    }
+    if (L == TILE_LINE) {  // 128 B line = 4 rows x 8 cols made of four 2x4 sectors
+        const int line = (px >> 2) * la.tiles_per_row + (py >> 3);
+        const int sector = ((px >> 1) & 1) * 2 + ((py >> 2) & 1);
+        return __ldg(la.tiled + ((line << 5) | (sector << 3) | ((px & 1) << 2) | (py & 3)));
+    }
+    if (L == TEX) return tex2D<float>(la.tex, (float)py + 0.5f, (float)px + 0.5f);
+    if (L == U16_4x4) {    // exact d^2 as u16 (valid when max d^2 < 65536), 32 B sector = 4x4 cells
+        const int idx = (((px >> 2) * la.tiles_per_row + (py >> 2)) << 4) | ((px & 3) << 2) | (py & 3);
+        return sqrtf((float)__ldg(la.d2u16 + idx));
+    }
+    return 0.f;
+}
+
+template <int L, int BS = 256>
+__global__ void __launch_bounds__(BS) k_ray(Args a, LayoutArgs la, int cap = 1 << 30)
+{
+    const unsigned i = blockIdx.x * (unsigned)BS + threadIdx.x;
+    const unsigned total = (unsigned)a.num_poses * a.num_beams;
+    if (i >= total) return;
+    const MarchParams &P = a.P;
+    const unsigned k = i / (unsigned)a.num_beams;
+    const int j = i - k * a.num_beams;
+    const float *p = a.poses + 3 * k;
+    const float thw = __ldg(p + 2);
+    const GridPose g = rl::world_to_grid(P.w, __ldg(p), __ldg(p + 1), thw);
+    float dx, dy;
+    rl::glibc_sincosf(beam_heading(a, thw, j), &dy, &dx);
+    const float x0 = g.y, y0 = g.x;
+    float t = 0.f, r = P.max_range;
+    int it = 0;
+    while (t < P.max_range) {
+        if (++it > cap) break;
+        const float fx = fmaf(dx, t, x0), fy = fmaf(dy, t, y0);
+        if (!(fx > -1.0f && fx < P.frows && fy > -1.0f && fy < P.fcols)) break;
+        const int px = __float2int_rz(fx), py = __float2int_rz(fy);
+        const float d = fetch<L>(P, la, px, py);
+        if (d <= 0.0f) {
+            const float xd = __fsub_rn((float)px, x0), yd = __fsub_rn((float)py, y0);
+            r = sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+            break;
+        }
+        t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+    }
+    a.outs[i] = __fmul_rn(r, P.w.scale);
+}
+
+// ---------------------------------------------------------------- V5: leaner thread-per-ray: magic-number
+// divide, host-computed beam increment, integer bounds test, hit distance computed once after the
+// loop has reconverged (not once per divergent exit group)
+struct Lean { uint32_t magic; int shift; float inc; };
+
+template <int BS, int RPL>
+__global__ void __launch_bounds__(BS) k_lean(Args a, Lean q, int cap)
+{
+    const MarchParams &P = a.P;
+    const unsigned total = (unsigned)a.num_poses * a.num_beams;
+    // RPL rays per lane: ray r of this lane is i0 + r*32 (a warp covers 32*RPL consecutive rays)
+    const unsigned warp_base = (blockIdx.x * (unsigned)BS + (threadIdx.x & ~31u)) * RPL + (threadIdx.x & 31u);
+    float dx[RPL], dy[RPL], x0[RPL], y0[RPL];
+    bool valid[RPL];
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+        const unsigned i = warp_base + 32u * r;
+        valid[r] = i < total;
+        const unsigned ii = valid[r] ? i : 0u;
+        const unsigned k = __umulhi(ii, q.magic) >> q.shift;
+        const int j = ii - k * a.num_beams;
+        const float *p = a.poses + 3 * k;
+        const float thw = __ldg(p + 2);
+        const GridPose g = rl::world_to_grid(P.w, __ldg(p), __ldg(p + 1), thw);
+        const float thg = __fadd_rn(-__fadd_rn(thw, fmaf((float)j, q.inc, -0.5f * a.fov)), P.w.rotation_const);
+        rl::glibc_sincosf(thg, &dy[r], &dx[r]);
+        x0[r] = g.y; y0[r] = g.x;
+    }
+    int hx[RPL], hy[RPL];   // hit cell, hx < 0: no hit (max range)
+    int cur = 0;
+    while (cur < RPL && !valid[cur]) ++cur;
+    float cdx = dx[0], cdy = dy[0], cx0 = x0[0], cy0 = y0[0], t = 0.f;
+#pragma unroll
+    for (int r = 1; r < RPL; ++r) if (cur == r) { cdx = dx[r]; cdy = dy[r]; cx0 = x0[r]; cy0 = y0[r]; }
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) hx[r] = -1;
+    int it = 0;
+    while (cur < RPL) {
+        bool done = false;
+        int px = -1, py = 0;
+        if (!(cdx == cdx) || !(cx0 == cx0) || !(cy0 == cy0) || ++it > cap) done = true;   // NaN pose/heading: leaves the map
+        else {
+            px = __float2int_rz(fmaf(cdx, t, cx0));
+            py = __float2int_rz(fmaf(cdy, t, cy0));
+            if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) { done = true; px = -1; }
+            else {
+                const float d = __ldg(P.dist + (px * P.cols + py));
+                if (d <= 0.0f) done = true;
+                else {
+                    t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+                    if (!(t < P.max_range)) { done = true; px = -1; }
+                }
+            }
+        }
+        if (done) {
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) if (cur == r) { hx[r] = px; hy[r] = py; }
+            ++cur;
+            t = 0.f; it = 0;
+#pragma unroll
+            for (int r = 1; r < RPL; ++r) if (cur == r) { cdx = dx[r]; cdy = dy[r]; cx0 = x0[r]; cy0 = y0[r]; if (!valid[r]) cur = RPL; }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+        const unsigned i = warp_base + 32u * r;
+        float res = P.max_range;
+        if (hx[r] >= 0) {
+            const float xd = __fsub_rn((float)hx[r], x0[r]), yd = __fsub_rn((float)hy[r], y0[r]);
+            res = sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+        }
+        if (valid[r]) a.outs[i] = __fmul_rn(res, P.w.scale);
+    }
+}
+
+// ---------------------------------------------------------------- V6: k_ray with minimal changes, one at a time
+// OPT bit0: magic divide + host inc; bit1: hit distance after the loop; bit2: integer bounds test
+template <int OPT>
+__global__ void __launch_bounds__(128) k_ray3(Args a, Lean q)
+{
+    const unsigned i = blockIdx.x * 128u + threadIdx.x;
+    const unsigned total = (unsigned)a.num_poses * a.num_beams;
+    if (i >= total) return;
+    const MarchParams &P = a.P;
+    unsigned k;
+    if (OPT & 1) k = __umulhi(i, q.magic) >> q.shift; else k = i / (unsigned)a.num_beams;
+    const int j = i - k * a.num_beams;
+    const float *p = a.poses + 3 * k;
+    const float thw = __ldg(p + 2);
+    const GridPose g = rl::world_to_grid(P.w, __ldg(p), __ldg(p + 1), thw);
+    const float inc = (OPT & 1) ? q.inc : a.fov / (float)a.num_beams;
+    const float thg = __fadd_rn(-__fadd_rn(thw, fmaf((float)j, inc, -0.5f * a.fov)), P.w.rotation_const);
+    float dx, dy;
+    rl::glibc_sincosf(thg, &dy, &dx);
+    const float x0 = g.y, y0 = g.x;
+    float t = 0.f, r = P.max_range;
+    int hx = -1, hy = 0;
+    const bool bad = !(x0 == x0) || !(y0 == y0) || !(dx == dx);
+    if (!bad) {
+        while (t < P.max_range) {
+            const float fx = fmaf(dx, t, x0), fy = fmaf(dy, t, y0);
+            int px, py;
+            if (OPT & 4) {
+                px = __float2int_rz(fx); py = __float2int_rz(fy);
+                if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) break;
+            } else {
+                if (!(fx > -1.0f && fx < P.frows && fy > -1.0f && fy < P.fcols)) break;
+                px = __float2int_rz(fx); py = __float2int_rz(fy);
+            }
+            const float d = __ldg(P.dist + (px * P.cols + py));
+            if (d <= 0.0f) {
+                if (OPT & 2) { hx = px; hy = py; }
+                else {
+                    const float xd = __fsub_rn((float)px, x0), yd = __fsub_rn((float)py, y0);
+                    r = sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+                }
+                break;
+            }
+            t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+        }
+    }
+    if ((OPT & 2) && hx >= 0) {
+        const float xd = __fsub_rn((float)hx, x0), yd = __fsub_rn((float)hy, y0);
+        r = sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+    }
+    a.outs[i] = __fmul_rn(r, P.w.scale);
+}
+
+// ---------------------------------------------------------------- harness
+static std::vector<char> slurp(const std::string &path)
+{
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) { printf("cannot open %s\n", path.c_str()); exit(1); }
+    fseek(f, 0, SEEK_END);
+    long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<char> b(n);
+    if (fread(b.data(), 1, n, f) != (size_t)n) exit(1);
+    fclose(f);
+    return b;
+}
+
+struct Runner {
+    Args a;
+    float *d_ref = nullptr;
+    size_t n_rays;
+    char *flush = nullptr;
+    int reps;
+    cudaEvent_t e0, e1;
+    std::vector<float> h_ref, h_out;
+
+    template <typename F> void run(const char *name, F launch, bool is_ref = false)
+    {
+        CK(cudaMemset(a.outs, 0xff, n_rays * 4));
+        float best = 1e30f, sum = 0.f;
+        for (int r = 0; r < reps + 2; ++r) {
+            CK(cudaMemsetAsync(flush, r, 256u << 20));
+            CK(cudaMemsetAsync(a.counter, 0, 4));
+            CK(cudaEventRecord(e0));
+            launch();
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            CK(cudaGetLastError());
+            float ms;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            if (r >= 2) { best = ms < best ? ms : best; sum += ms; }
+        }
+        CK(cudaMemcpy(h_out.data(), a.outs, n_rays * 4, cudaMemcpyDeviceToHost));
+        size_t bad = 0;
+        if (is_ref) h_ref = h_out;
+        else for (size_t i = 0; i < n_rays; ++i) bad += memcmp(&h_out[i], &h_ref[i], 4) != 0;
+        printf("%-44s mean %8.2f us  best %8.2f us  %7.2f Grays/s  mismatches %zu\n", name, sum / reps * 1e3,
+               best * 1e3, n_rays / (sum / reps * 1e-3) / 1e9, bad);
+        fflush(stdout);
+    }
+};
+
+int main(int argc, char **argv)
+{
+    std::string dir = argc > 1 ? argv[1] : "/tmp/tune";
+    int reps = argc > 2 ? atoi(argv[2]) : 20;
+    auto meta = slurp(dir + "/meta.bin");   // int32 rows, cols, num_poses, num_beams; float max_range, fov; WorldFrame
+    auto dist = slurp(dir + "/dist.bin");
+    auto poses = slurp(dir + "/poses.bin");
+    const int32_t *mi = (const int32_t *)meta.data();
+    const float *mf = (const float *)(meta.data() + 16);
+    Runner R;
+    Args &a = R.a;
+    a.P.rows = mi[0]; a.P.cols = mi[1]; a.num_poses = mi[2]; a.num_beams = mi[3];
+    a.P.frows = (float)a.P.rows; a.P.fcols = (float)a.P.cols;
+    a.P.max_range = mf[0]; a.fov = mf[1];
+    memcpy(&a.P.w, mf + 2, sizeof(rl::WorldFrame));
+    R.n_rays = (size_t)a.num_poses * a.num_beams;
+    R.reps = reps;
+    float *d_dist, *d_poses;
+    CK(cudaMalloc(&d_dist, dist.size())); CK(cudaMemcpy(d_dist, dist.data(), dist.size(), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_poses, poses.size())); CK(cudaMemcpy(d_poses, poses.data(), poses.size(), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&a.outs, R.n_rays * 4));
+    CK(cudaMalloc(&a.counter, 4));
+    CK(cudaMalloc(&R.flush, 256u << 20));
+    CK(cudaEventCreate(&R.e0)); CK(cudaEventCreate(&R.e1));
+    a.P.dist = d_dist; a.poses = d_poses;
+    R.h_out.resize(R.n_rays);
+    int sms; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+    printf("map %dx%d, %d poses x %d beams, %d SMs, reps %d\n", a.P.rows, a.P.cols, a.num_poses, a.num_beams, sms, reps);
+
+    const bool quick = argc > 3;
+    const int groups = (a.num_beams + 31) / 32;
+    auto base = [&](auto wpc_tag, int segs_target) {
+        constexpr int WPC = decltype(wpc_tag)::value;
+        int s = segs_target < 1 ? 1 : (segs_target > groups ? groups : segs_target);
+        int gl = (groups + s - 1) / s, seg_len = gl * 32, segs = (groups + gl - 1) / gl;
+        long warps = (long)a.num_poses * segs;
+        k_base<WPC><<<(unsigned)((warps + WPC - 1) / WPC), WPC * 32>>>(a, segs, seg_len);
+    };
+    R.run("base wpc8 segs5 (product)", [&] { base(std::integral_constant<int, 8>{}, 5); }, true);
+    if (!quick) {
+    R.run("base wpc8 segs1 (warp per pose)", [&] { base(std::integral_constant<int, 8>{}, 1); });
+    R.run("base wpc8 segs9", [&] { base(std::integral_constant<int, 8>{}, 9); });
+    R.run("base wpc8 segs34 (32 beams/warp)", [&] { base(std::integral_constant<int, 8>{}, 34); });
+    R.run("base wpc4 segs5", [&] { base(std::integral_constant<int, 4>{}, 5); });
+    R.run("base wpc2 segs5", [&] { base(std::integral_constant<int, 2>{}, 5); });
+    R.run("base wpc2 segs17", [&] { base(std::integral_constant<int, 2>{}, 17); });
+    R.run("base wpc1 segs5", [&] { base(std::integral_constant<int, 1>{}, 5); });
+
+#define PERSIST(ILP, WPC, BPS) R.run("persist ilp" #ILP " wpc" #WPC " blocks/SM " #BPS, [&] { \
+        k_persist<ILP, WPC><<<sms * BPS, WPC * 32>>>(a, (a.num_beams + 32 * ILP - 1) / (32 * ILP)); })
+    PERSIST(1, 8, 8); PERSIST(1, 4, 16); PERSIST(1, 8, 4);
+    PERSIST(2, 8, 8); PERSIST(2, 8, 4); PERSIST(2, 4, 16); PERSIST(2, 8, 6);
+    PERSIST(4, 8, 4); PERSIST(4, 8, 2); PERSIST(4, 8, 8); PERSIST(3, 8, 6);
+
+#define FLAT(NB, WPC, BPS) R.run("flat nb" #NB " wpc" #WPC " blocks/SM " #BPS, [&] { \
+        k_flat<NB, WPC><<<sms * BPS, WPC * 32>>>(a, (a.num_beams + 32 * NB - 1) / (32 * NB)); })
+    FLAT(2, 8, 8); FLAT(4, 8, 8); FLAT(4, 8, 6); FLAT(6, 8, 6); FLAT(8, 8, 4); FLAT(8, 8, 8); FLAT(4, 4, 16);
+
+#define CTAPOSE(ILP, WPC, BPS) R.run("cta-per-pose ilp" #ILP " wpc" #WPC " blocks/SM " #BPS, [&] { \
+        k_cta_pose<ILP, WPC><<<sms * BPS, WPC * 32>>>(a, (a.num_beams + 32 * ILP - 1) / (32 * ILP)); })
+    CTAPOSE(1, 8, 8); CTAPOSE(1, 4, 16); CTAPOSE(2, 4, 16); CTAPOSE(2, 8, 8); CTAPOSE(2, 8, 4); CTAPOSE(1, 16, 4);
+    CTAPOSE(2, 16, 4); CTAPOSE(1, 2, 32); CTAPOSE(2, 2, 32);
+    }
+
+    // ---- lean variants ----
+    {
+        Lean q;
+        // magic for unsigned division by num_beams valid for all 32-bit numerators: ceil(2^(32+s)/d)
+        // exact for numerators < 2^31: k = umulhi(i, ceil(2^(31+s)/d)) >> (s-1), s = ceil(log2 d) >= 1
+        int sft = 1; while ((1u << sft) < (unsigned)a.num_beams) ++sft;
+        unsigned long long m = ((1ull << (31 + sft)) + a.num_beams - 1) / a.num_beams;
+        bool ok = m <= 0xffffffffull && R.n_rays < (1ull << 31);
+        sft -= 1;
+        if (!ok) { printf("magic overflow, need 33-bit path\n"); }
+        q.magic = (uint32_t)m; q.shift = sft; q.inc = a.fov / (float)a.num_beams;
+        auto nb = [&](int bs, int rpl) { return (unsigned)((R.n_rays + (size_t)bs * rpl - 1) / ((size_t)bs * rpl)); };
+        if (ok) {
+        unsigned b3 = (unsigned)((R.n_rays + 127) / 128);
+        R.run("ray3 opt0", [&] { k_ray3<0><<<b3, 128>>>(a, q); });
+        R.run("ray3 opt1 magic", [&] { k_ray3<1><<<b3, 128>>>(a, q); });
+        R.run("ray3 opt2 hit-after", [&] { k_ray3<2><<<b3, 128>>>(a, q); });
+        R.run("ray3 opt4 int-bounds", [&] { k_ray3<4><<<b3, 128>>>(a, q); });
+        R.run("ray3 opt3", [&] { k_ray3<3><<<b3, 128>>>(a, q); });
+        R.run("ray3 opt7", [&] { k_ray3<7><<<b3, 128>>>(a, q); });
+        R.run("ray3 opt5", [&] { k_ray3<5><<<b3, 128>>>(a, q); });
+        R.run("lean bs128 rpl1", [&] { k_lean<128, 1><<<nb(128, 1), 128>>>(a, q, 1 << 30); });
+        R.run("lean bs256 rpl1", [&] { k_lean<256, 1><<<nb(256, 1), 256>>>(a, q, 1 << 30); });
+        R.run("lean bs128 rpl2", [&] { k_lean<128, 2><<<nb(128, 2), 128>>>(a, q, 1 << 30); });
+        R.run("lean bs64 rpl2", [&] { k_lean<64, 2><<<nb(64, 2), 64>>>(a, q, 1 << 30); });
+        R.run("lean bs128 rpl3", [&] { k_lean<128, 3><<<nb(128, 3), 128>>>(a, q, 1 << 30); });
+        R.run("lean bs128 rpl4", [&] { k_lean<128, 4><<<nb(128, 4), 128>>>(a, q, 1 << 30); });
+        R.run("lean bs64 rpl4", [&] { k_lean<64, 4><<<nb(64, 4), 64>>>(a, q, 1 << 30); });
+        R.run("lean bs128 rpl1 cap32 (timing only)", [&] { k_lean<128, 1><<<nb(128, 1), 128>>>(a, q, 32); });
+        R.run("lean bs128 rpl2 cap32 (timing only)", [&] { k_lean<128, 2><<<nb(128, 2), 128>>>(a, q, 32); });
+        }
+    }
+    // ---- alternative layouts ----
+    {
+        const int rows = a.P.rows, cols = a.P.cols;
+        const float *hd = (const float *)dist.data();
+        auto build = [&](int th, int tw, bool line, int *tpr) {
+            int TH = line ? 4 : th, TW = line ? 8 : tw;
+            int trows = (rows + TH - 1) / TH, tcols = (cols + TW - 1) / TW;
+            *tpr = tcols;
+            std::vector<float> t((size_t)trows * tcols * TH * TW, 0.f);
+            for (int px = 0; px < rows; ++px)
+                for (int py = 0; py < cols; ++py) {
+                    size_t idx;
+                    if (line) {
+                        size_t ln = (size_t)(px >> 2) * tcols + (py >> 3);
+                        int sector = ((px >> 1) & 1) * 2 + ((py >> 2) & 1);
+                        idx = (ln << 5) | (sector << 3) | ((px & 1) << 2) | (py & 3);
+                    } else {
+                        int lh = th == 2 ? 1 : 2, lw = tw == 4 ? 2 : 1;
+                        idx = ((((size_t)(px >> lh)) * tcols + (py >> lw)) << 3) | ((px & (th - 1)) << lw) | (py & (tw - 1));
+                    }
+                    t[idx] = hd[(size_t)px * cols + py];
+                }
+            float *d;
+            CK(cudaMalloc(&d, t.size() * 4));
+            CK(cudaMemcpy(d, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+            return d;
+        };
+        unsigned blocks = (unsigned)((R.n_rays + 255) / 256);
+        LayoutArgs la{};
+        R.run("ray rowmajor (new product)", [&] { k_ray<ROWMAJOR><<<blocks, 256>>>(a, la); });
+        R.run("ray rowmajor bs64", [&] { k_ray<ROWMAJOR, 64><<<(unsigned)((R.n_rays + 63) / 64), 64>>>(a, la); });
+        R.run("ray rowmajor bs128", [&] { k_ray<ROWMAJOR, 128><<<(unsigned)((R.n_rays + 127) / 128), 128>>>(a, la); });
+        R.run("ray rowmajor bs512", [&] { k_ray<ROWMAJOR, 512><<<(unsigned)((R.n_rays + 511) / 512), 512>>>(a, la); });
+        R.run("ray rowmajor bs32", [&] { k_ray<ROWMAJOR, 32><<<(unsigned)((R.n_rays + 31) / 32), 32>>>(a, la); });
+        R.run("ray rowmajor cap 8 (timing only)", [&] { k_ray<ROWMAJOR><<<blocks, 256>>>(a, la, 8); });
+        R.run("ray rowmajor cap 16 (timing only)", [&] { k_ray<ROWMAJOR><<<blocks, 256>>>(a, la, 16); });
+        R.run("ray rowmajor cap 32 (timing only)", [&] { k_ray<ROWMAJOR><<<blocks, 256>>>(a, la, 32); });
+        R.run("ray rowmajor cap 64 (timing only)", [&] { k_ray<ROWMAJOR><<<blocks, 256>>>(a, la, 64); });
+        R.run("ray rowmajor cap 128 (timing only)", [&] { k_ray<ROWMAJOR><<<blocks, 256>>>(a, la, 128); });
+        R.run("ray rowmajor bs64 cap 32 (timing only)", [&] { k_ray<ROWMAJOR, 64><<<(unsigned)((R.n_rays + 63) / 64), 64>>>(a, la, 32); });
+        la.tiled = build(2, 4, false, &la.tiles_per_row);
+        R.run("ray tiled 2x4 sectors", [&] { k_ray<TILE_2x4><<<blocks, 256>>>(a, la); });
+        la.tiled = build(4, 2, false, &la.tiles_per_row);
+        R.run("ray tiled 4x2 sectors", [&] { k_ray<TILE_4x2><<<blocks, 256>>>(a, la); });
+        la.tiled = build(0, 0, true, &la.tiles_per_row);
+        R.run("ray tiled line 4x8 of 2x4 sectors", [&] { k_ray<TILE_LINE><<<blocks, 256>>>(a, la); });
+        // texture (block-linear cudaArray, point sampling)
+        {
+            cudaArray_t arr;
+            cudaChannelFormatDesc cd = cudaCreateChannelDesc<float>();
+            CK(cudaMallocArray(&arr, &cd, cols, rows));
+            CK(cudaMemcpy2DToArray(arr, 0, 0, hd, (size_t)cols * 4, (size_t)cols * 4, rows, cudaMemcpyHostToDevice));
+            cudaResourceDesc rd{}; rd.resType = cudaResourceTypeArray; rd.res.array.array = arr;
+            cudaTextureDesc td{}; td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+            td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+            CK(cudaCreateTextureObject(&la.tex, &rd, &td, nullptr));
+            R.run("ray texture (cudaArray, point)", [&] { k_ray<TEX><<<blocks, 256>>>(a, la); });
+        }
+        // u16 d^2, 4x4 per sector
+        {
+            int trows = (rows + 3) / 4, tcols = (cols + 3) / 4;
+            la.tiles_per_row = tcols;
+            std::vector<unsigned short> t((size_t)trows * tcols * 16, 0);
+            float mx = 0;
+            for (int px = 0; px < rows; ++px)
+                for (int py = 0; py < cols; ++py) {
+                    float d = hd[(size_t)px * cols + py];
+                    mx = d > mx ? d : mx;
+                    long d2 = lroundf(d * d);
+                    size_t idx = ((((size_t)(px >> 2)) * tcols + (py >> 2)) << 4) | ((px & 3) << 2) | (py & 3);
+                    t[idx] = (unsigned short)(d2 > 65535 ? 65535 : d2);
+                }
+            unsigned short *d;
+            CK(cudaMalloc(&d, t.size() * 2));
+            CK(cudaMemcpy(d, t.data(), t.size() * 2, cudaMemcpyHostToDevice));
+            la.d2u16 = d;
+            printf("max dist %.2f px\n", mx);
+            R.run("ray u16 d^2 tiled 4x4 + sqrt", [&] { k_ray<U16_4x4><<<blocks, 256>>>(a, la); });
+        }
+    }
+    return 0;
+}
