@@ -203,22 +203,35 @@ int32_t host_pipeline(rl_marcher *m, const float *ins, int64_t in_stride_floats,
             src = m->h_in;
         }
         float *dst = out_pinned ? outs + b * out_floats : m->h_out;
-        // sub-chunks of >= 256K ranges, at most 16 per chunk
-        int64_t nsub = (c * out_floats) >> 18;
-        nsub = nsub < 1 ? 1 : (nsub > 16 ? 16 : nsub);
+        // a few sub-chunks of >= 512K ranges: every async call costs microseconds of host time, so
+        // the pipeline is kept shallow; small inputs (the fan's 12 B/pose) go up in one copy
+        int64_t nsub = (c * out_floats) >> 19;
+        nsub = nsub < 1 ? 1 : (nsub > 6 ? 6 : nsub);
         if (nsub > c) nsub = c;
         const int64_t per = (c + nsub - 1) / nsub;
+        const bool one_h2d = (size_t)c * in_floats * sizeof(float) <= ((size_t)1 << 20);
+        cudaEvent_t up = nullptr;
+        if (one_h2d) {
+            RL_CUDA(cudaMemcpyAsync(m->d_in, src, (size_t)c * in_floats * sizeof(float), cudaMemcpyHostToDevice, st[0]));
+            if (nsub > 1) {
+                RL_CUDA(cudaEventCreateWithFlags(&up, cudaEventDisableTiming));
+                RL_CUDA(cudaEventRecord(up, st[0]));
+                RL_CUDA(cudaStreamWaitEvent(st[1], up, 0));
+            }
+        }
         int i = 0;
         for (int64_t u = 0; u < c; u += per, ++i) {
             const int64_t n = (c - u < per) ? c - u : per;
             cudaStream_t s = st[i & 1];
-            RL_CUDA(cudaMemcpyAsync(m->d_in + u * in_floats, src + u * in_floats, (size_t)n * in_floats * sizeof(float),
-                                    cudaMemcpyHostToDevice, s));
+            if (!one_h2d)
+                RL_CUDA(cudaMemcpyAsync(m->d_in + u * in_floats, src + u * in_floats, (size_t)n * in_floats * sizeof(float),
+                                        cudaMemcpyHostToDevice, s));
             rc = launch(u, n, m->d_in + u * in_floats, m->d_out + u * out_floats, s);
-            if (rc != RL_OK) return rc;
+            if (rc != RL_OK) { if (up) cudaEventDestroy(up); return rc; }
             RL_CUDA(cudaMemcpyAsync(dst + u * out_floats, m->d_out + u * out_floats, (size_t)n * out_floats * sizeof(float),
                                     cudaMemcpyDeviceToHost, s));
         }
+        if (up) cudaEventDestroy(up);
         RL_CUDA(cudaStreamSynchronize(st[0]));
         RL_CUDA(cudaStreamSynchronize(st[1]));
         if (!out_pinned) std::memcpy(outs + b * out_floats, m->h_out, (size_t)c * out_floats * sizeof(float));
