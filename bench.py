@@ -43,7 +43,9 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--poses", type=int, default=4096, help="poses per GPU per step")
     ap.add_argument("--beams", type=int, default=1080)
-    ap.add_argument("--gather", default="allgather", choices=["allgather", "none"])
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "allgather", "none"],
+                    help="N>1: p2p = march kernel stores into every GPU's gathered buffer over NVLink (fused); "
+                         "allgather = march then NCCL all_gather; none = ranges stay sharded")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps")
     return ap.parse_args()
@@ -199,6 +201,11 @@ def run_native(args, rank, world, local_rank):
     d_out = torch.empty(n_rays, dtype=torch.float32, device=dev)
     d_all = torch.empty(world * n_rays, dtype=torch.float32, device=dev) if dist_on and args.gather == "allgather" else None
     rm = range_libc.PyRayMarchingGPU(omap, MAX_RANGE_PX)
+    peer = None
+    if dist_on and args.gather == "p2p":
+        from pyracecarsimulator_b200.sharded import PeerGather
+        peer = PeerGather(local_rank, n_rays)
+        stream_ptr = int(torch.cuda.current_stream(local_rank).cuda_stream)
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def step(i, ev0=None, ev1=None):
@@ -206,9 +213,13 @@ def run_native(args, rank, world, local_rank):
             flush.fill_(i & 0xFF)          # 256 MiB write > 126 MB L2: evicts the distance field
         if ev0 is not None:
             ev0.record()
-        rm.calc_range_fan(d_poses[i % n_sets], d_out, FOV, B)
-        if d_all is not None:
-            tdist.all_gather_into_tensor(d_all, d_out)
+        if peer is not None:
+            peer.march(rm, d_poses[i % n_sets], FOV, B, stream_ptr)   # fused march + all-gather
+            peer.sync()
+        else:
+            rm.calc_range_fan(d_poses[i % n_sets], d_out, FOV, B)
+            if d_all is not None:
+                tdist.all_gather_into_tensor(d_all, d_out)
         if ev1 is not None:
             ev1.record()
 
@@ -226,6 +237,15 @@ def run_native(args, rank, world, local_rank):
     barrier()
     t_wall = time.perf_counter() - t_wall0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    if peer is not None:   # correctness of the fused gather: slot r of every buffer == rank r's own scan
+        peer.march(rm, d_poses[0], FOV, B, stream_ptr)
+        peer.sync()
+        rm.calc_range_fan(d_poses[0], d_out, FOV, B)
+        mine = [torch.empty_like(d_out) for _ in range(world)]
+        tdist.all_gather(mine, d_out)
+        torch.cuda.synchronize()
+        if not torch.equal(peer.tensor(), torch.cat(mine)):
+            raise SystemExit("bench.py: fused p2p gather differs from march + NCCL all_gather")
     launches = K  # one march kernel per step (flush fills and NCCL kernels are not ours)
 
     # ---- e2e through the reference-facing API with host buffers ----
@@ -332,7 +352,9 @@ def run_native(args, rank, world, local_rank):
                        "global_rays_per_step": total_rays, "map": f"{MAP_N}x{MAP_N} fp32 distance field "
                        f"({dist_field.nbytes >> 20} MiB, replicated per GPU)",
                        "parallelism": f"pose-sharded x{world}, map replicated" +
-                                      (", NCCL all_gather of ranges inside the step" if d_all is not None else ""),
+                                      (", NCCL all_gather of ranges inside the step" if d_all is not None else "") +
+                                      (", ranges stored into every GPU's gathered buffer over NVLink by the march kernel "
+                                       "(fused all-gather) + 4-byte all_reduce as barrier, inside the step" if peer is not None else ""),
                        "l2": "no flush" if args.no_flush else "flushed between steps (256 MiB fill), fill excluded from the per-step events",
                        "timing": "CUDA events per step on the launching stream, summed, max over ranks",
                        "trig": "exact (sincosf per beam)"},
@@ -346,6 +368,8 @@ def run_native(args, rank, world, local_rank):
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))
+    if peer is not None:
+        peer.close()
     if dist_on:
         tdist.barrier()
         tdist.destroy_process_group()

@@ -139,6 +139,22 @@ RL_API int32_t rl_calc_range_repeat_angles(rl_marcher *m, const float *d_poses, 
 RL_API int32_t rl_calc_range_repeat_angles_host(rl_marcher *m, const float *poses, const float *angles,
                                          float *outs, int64_t num_poses, int32_t num_angles);
 
+/* ---- fused march + all-gather over NVLink peer memory (one process per GPU) ---- */
+/* rl_peer_alloc: device buffer + 64-byte CUDA IPC handle to hand to the other ranks;           */
+/* rl_peer_open: map another rank's buffer into this process (peer access enabled lazily).      */
+RL_API int32_t rl_peer_alloc(int32_t device, int64_t bytes, void **d_ptr, uint8_t *handle64);
+RL_API int32_t rl_peer_open(int32_t device, const uint8_t *handle64, void **d_ptr);
+RL_API int32_t rl_peer_close(int32_t device, void *d_ptr);
+RL_API int32_t rl_peer_free(int32_t device, void *d_ptr);
+/* rl_calc_range_fan with the all-gather fused in: every range is stored straight into slot      */
+/* `rank` (offset rank*slot_rays) of each of the `world` gathered buffers peer_bufs[0..world)     */
+/* (peer_bufs is a HOST array of device pointers as mapped in this process).  Ranks synchronise  */
+/* afterwards with any stream-ordered collective before reading.                                 */
+RL_API int32_t rl_calc_range_fan_allgather(rl_marcher *m, const float *d_poses, int64_t pose_stride_rows,
+                                           void *const *peer_bufs, int32_t world, int32_t rank,
+                                           int64_t slot_rays, int64_t num_poses, int32_t num_rays,
+                                           float fov, void *stream);
+
 /* Number of distance-field loads ("march steps") the last *_host call performed, when the */
 /* marcher was asked to count them (rl_marcher_count_steps(m, 1)); used by the roofline.    */
 RL_API int32_t rl_marcher_count_steps(rl_marcher *m, int32_t enable);

@@ -58,6 +58,11 @@ SIGNATURES = {
     "rl_calc_range_fan_host": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _f]),
     "rl_calc_range_repeat_angles": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "rl_calc_range_repeat_angles_host": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32]),
+    "rl_peer_alloc": (_i32, [_i32, _i64, C.POINTER(_vp), _vp]),
+    "rl_peer_open": (_i32, [_i32, _vp, C.POINTER(_vp)]),
+    "rl_peer_close": (_i32, [_i32, _vp]),
+    "rl_peer_free": (_i32, [_i32, _vp]),
+    "rl_calc_range_fan_allgather": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _i64, _i64, _i32, _f, _vp]),
     "rl_marcher_count_steps": (_i32, [_vp, _i32]),
     "rl_marcher_last_steps": (_i32, [_vp, C.POINTER(C.c_uint64)]),
     "rl_car_create": (_i32, [_vp, _i32, C.POINTER(_vp)]),

@@ -48,11 +48,22 @@ march_many_kernel(MarchParams P, const float *__restrict__ ins, float *__restric
 // by L2 sector throughput and the hardware CTA scheduler is the cheapest load balancer.
 // FAN:   beam j heads theta + fmaf(j, fov/num_beams, -fov/2)   (fork's 4-arg calc_range_many)
 // !FAN:  beam a heads theta + angles[a]                        (calc_range_repeat_angles)
-template <bool FAN, bool COUNT, bool SMALL>
+// Peer output: the fused march + all-gather writes every range straight into the gathered buffer
+// of every GPU of the box (its own included) over NVLink, so the transfer overlaps the march ray by
+// ray instead of following it as a separate collective.
+constexpr int MAX_PEERS = 16;
+struct PeerOut {
+    float *buf[MAX_PEERS];   // gathered buffer of each rank (peer-mapped device pointers)
+    int world;
+    int64_t offset;          // this rank's slot: rank * slot_rays
+};
+
+template <bool FAN, bool COUNT, bool SMALL, bool PEERS = false>
 __global__ void __launch_bounds__(CTA_THREADS)
 march_pose_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_stride_floats,
                   const float *__restrict__ angles, float *__restrict__ outs, int64_t num_rays_total,
-                  int num_beams, rl::FastDiv div, float fov, float inc, unsigned long long *counter)
+                  int num_beams, rl::FastDiv div, float fov, float inc, unsigned long long *counter,
+                  PeerOut peers = PeerOut{})
 {
     const int64_t i = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
     uint32_t steps = 0;
@@ -75,7 +86,13 @@ march_pose_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_s
         else thg = __fsub_rn(g.theta, __ldg(angles + j));
         float s, c;
         rl::glibc_sincosf(thg, &s, &c);
-        outs[i] = __fmul_rn(rl::march_ray<COUNT>(P, g.y, g.x, c, s, steps), P.w.scale);
+        const float r = __fmul_rn(rl::march_ray<COUNT>(P, g.y, g.x, c, s, steps), P.w.scale);
+        if (PEERS) {
+#pragma unroll 1
+            for (int q = 0; q < peers.world; ++q) peers.buf[q][peers.offset + i] = r;
+        } else {
+            outs[i] = r;
+        }
     }
     flush_steps<COUNT>(steps, counter);
 }
@@ -344,6 +361,84 @@ int32_t rl_calc_range_repeat_angles(rl_marcher *m, const float *d_poses, const f
     rl::DeviceGuard guard(m->map->device);
     return launch_pose<false>(m, d_poses, 1, d_angles, d_outs, num_poses, num_angles, 0.0f,
                               (cudaStream_t)stream);
+}
+
+// ---- peer memory for the fused march + all-gather (one process per GPU) ----
+int32_t rl_peer_alloc(int32_t device, int64_t bytes, void **d_ptr, uint8_t *handle64)
+{
+    if (!d_ptr || !handle64 || bytes <= 0) return rl::fail(RL_ERR_BAD_ARG, "rl_peer_alloc: bad argument");
+    rl::DeviceGuard guard(device);
+    if (!guard.ok) return rl::fail(RL_ERR_NO_DEVICE, "rl_peer_alloc: bad device");
+    void *p = nullptr;
+    RL_CUDA(cudaMalloc(&p, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return rl::fail(RL_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(handle64, &h, 64);
+    *d_ptr = p;
+    return RL_OK;
+}
+
+int32_t rl_peer_open(int32_t device, const uint8_t *handle64, void **d_ptr)
+{
+    if (!d_ptr || !handle64) return rl::fail(RL_ERR_BAD_ARG, "rl_peer_open: bad argument");
+    rl::DeviceGuard guard(device);
+    if (!guard.ok) return rl::fail(RL_ERR_NO_DEVICE, "rl_peer_open: bad device");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, 64);
+    RL_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return RL_OK;
+}
+
+int32_t rl_peer_close(int32_t device, void *d_ptr)
+{
+    rl::DeviceGuard guard(device);
+    RL_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return RL_OK;
+}
+
+int32_t rl_peer_free(int32_t device, void *d_ptr)
+{
+    rl::DeviceGuard guard(device);
+    RL_CUDA(cudaFree(d_ptr));
+    return RL_OK;
+}
+
+// Fan march of this rank's poses with every range stored into slot `rank` of the gathered buffer
+// of all `world` GPUs: peer_bufs[q] is rank q's buffer (world * slot_rays floats) as mapped in THIS
+// process (own buffer for q == rank).  The caller synchronises the ranks afterwards (any
+// stream-ordered collective, e.g. a barrier) before anyone reads the gathered ranges.
+int32_t rl_calc_range_fan_allgather(rl_marcher *m, const float *d_poses, int64_t pose_stride_rows,
+                                    void *const *peer_bufs, int32_t world, int32_t rank, int64_t slot_rays,
+                                    int64_t num_poses, int32_t num_rays, float fov, void *stream)
+{
+    if (!m || !peer_bufs || world < 1 || world > MAX_PEERS || rank < 0 || rank >= world || num_poses < 0 ||
+        num_rays <= 0 || pose_stride_rows < 1 || num_poses * num_rays > slot_rays || (num_poses > 0 && !d_poses))
+        return rl::fail(RL_ERR_BAD_ARG, "rl_calc_range_fan_allgather: bad argument");
+    if (num_poses == 0) return RL_OK;
+    rl::DeviceGuard guard(m->map->device);
+    PeerOut po{};
+    for (int q = 0; q < world; ++q) {
+        if (!peer_bufs[q]) return rl::fail(RL_ERR_BAD_ARG, "rl_calc_range_fan_allgather: null peer buffer");
+        po.buf[q] = static_cast<float *>(peer_bufs[q]);
+    }
+    po.world = world;
+    po.offset = (int64_t)rank * slot_rays;
+    const int64_t total = num_poses * num_rays;
+    const int64_t blocks = (total + CTA_THREADS - 1) / CTA_THREADS;
+    if (blocks > 0x7fffffffLL) return rl::fail(RL_ERR_BAD_ARG, "rl_calc_range_fan_allgather: too many rays for one call");
+    const rl::FastDiv div = make_fast_div(num_rays);
+    const float inc = fov / (float)num_rays;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (num_rays >= 2 && total < ((int64_t)1 << 31))
+        march_pose_kernel<true, false, true, true><<<(unsigned)blocks, CTA_THREADS, 0, s>>>(
+            m->P, d_poses, pose_stride_rows * 3, nullptr, nullptr, total, num_rays, div, fov, inc, nullptr, po);
+    else
+        march_pose_kernel<true, false, false, true><<<(unsigned)blocks, CTA_THREADS, 0, s>>>(
+            m->P, d_poses, pose_stride_rows * 3, nullptr, nullptr, total, num_rays, div, fov, inc, nullptr, po);
+    RL_CUDA(cudaGetLastError());
+    return RL_OK;
 }
 
 int32_t rl_calc_range_many_host(rl_marcher *m, const float *ins, float *outs, int64_t n)

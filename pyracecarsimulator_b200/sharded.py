@@ -25,6 +25,80 @@ def shard_bounds(n: int, world: int, rank: int):
     return lo, hi
 
 
+class _DevicePtr:
+    """Zero-copy torch view of a raw device allocation (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, n_floats: int):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+class PeerGather:
+    """The fused march + all-gather: one gathered-ranges buffer per GPU (``world * slot_rays`` floats),
+    allocated by the C ABI, exchanged between the ranks as CUDA IPC handles and mapped into every
+    process, so that ``rl_calc_range_fan_allgather`` can store each range straight into slot ``rank`` of
+    all ``world`` buffers over NVLink while it marches (no separate collective, no staging copy).
+    ``sync()`` is the stream-ordered barrier after which every rank may read ``tensor()``."""
+
+    def __init__(self, device_index: int, slot_rays: int, group: Optional[dist.ProcessGroup] = None):
+        import ctypes as C
+        from . import _native
+        self._native = _native
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.device_index = int(device_index)
+        self.slot_rays = int(slot_rays)
+        L = _native.lib()
+        own = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        _native.check(L.rl_peer_alloc(self.device_index, self.world * self.slot_rays * 4, C.byref(own), handle),
+                      "rl_peer_alloc")
+        self._own = own
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self._opened = []
+        ptrs = []
+        for q in range(self.world):
+            if q == self.rank:
+                ptrs.append(own.value)
+                continue
+            p = C.c_void_p()
+            buf = (C.c_uint8 * 64).from_buffer_copy(handles[q])
+            _native.check(L.rl_peer_open(self.device_index, buf, C.byref(p)), "rl_peer_open")
+            self._opened.append(p)
+            ptrs.append(p.value)
+        self.ptrs = (C.c_void_p * self.world)(*ptrs)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=f"cuda:{self.device_index}")
+        self._view = torch.as_tensor(_DevicePtr(own.value, self.world * self.slot_rays),
+                                     device=f"cuda:{self.device_index}")
+
+    def tensor(self) -> torch.Tensor:
+        """This GPU's gathered buffer: (world * slot_rays,) float32, slot r = ranges of rank r."""
+        return self._view
+
+    def march(self, marcher, poses: torch.Tensor, fov: float, num_rays: int, stream_ptr: int):
+        n = poses.shape[0]
+        self._native.check(self._native.lib().rl_calc_range_fan_allgather(
+            marcher._h, poses.data_ptr(), 1, self.ptrs, self.world, self.rank, self.slot_rays, n, int(num_rays),
+            float(fov), stream_ptr), "rl_calc_range_fan_allgather")
+
+    def sync(self):
+        """Stream-ordered barrier: returns (on the stream) once every rank's march has completed."""
+        dist.all_reduce(self._flag, group=self.group)
+
+    def close(self):
+        L = self._native.lib()
+        dist.barrier(group=self.group)
+        for p in self._opened:
+            L.rl_peer_close(self.device_index, p)
+        self._opened = []
+        if self._own is not None:
+            self._view = None
+            L.rl_peer_free(self.device_index, self._own)
+            self._own = None
+
+
 def gpu_march_fn(marcher, fov: float, num_rays: int) -> Callable:
     """The product march: ``PyRayMarchingGPU.calc_range_fan`` on device tensors."""
     def run(poses: torch.Tensor, out: torch.Tensor):

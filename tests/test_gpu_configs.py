@@ -1,0 +1,91 @@
+"""BASELINE.json configs 3-5 as parity cases (config 1 and 2 live in test_gpu_scan_simulator.py and
+test_gpu_march.py): full-size runs checked against the oracle where it finishes in seconds, and
+through size-independent properties (determinism, permutation equivariance, subset == oracle)
+where it does not."""
+import numpy as np
+import pytest
+
+from pyracecarsimulator_b200 import maps, range_libc
+from pyracecarsimulator_b200.racecar import BatchedCar
+from gpu_util import assert_ranges_match, build_synth
+
+pytestmark = pytest.mark.gpu
+FOV = 4.71
+
+
+def test_config3_particle_filter_full_size(orc):
+    """1 M poses x 60 angles via calc_range_repeat_angles on the big-teach stand-in (2049^2)."""
+    omap, y, occ, dist = build_synth(orc, 2049, 1234)
+    rm = range_libc.PyRayMarchingGPU(omap, 300)
+    n, a = 1_000_000, 60
+    poses = maps.sample_free_poses(dist, n, 303, y.resolution, y.origin)
+    angles = np.linspace(-FOV / 2, FOV / 2, a, endpoint=False).astype(np.float32)
+    out = np.zeros(n * a, np.float32)
+    rm.calc_range_repeat_angles(poses, angles, out)
+    want = orc.Marcher(dist, 300, y.resolution, y.origin).calc_range_repeat_angles(poses, angles, threads=0)
+    assert_ranges_match(out, want, y.resolution)
+
+
+def test_config4_fused_rollout_full_size(orc, colombia, colombia_scan):
+    """65 536 cars x 50 steps x 1080 beams on maps/colombia: 3.54 G rays, nothing materialised.
+    Checked on a random subset of cars against the oracle, plus determinism."""
+    import torch
+    binar = np.where(colombia_scan["grid"] > 0, 255, 0).ravel()
+    omap = range_libc.PyOMap(maps.OccupancyGrid.make(binar, 435, 350, colombia["resolution"], colombia["origin"]))
+    dist = orc.edt_float(colombia_scan["occ"])
+    rm = range_libc.PyRayMarchingGPU(omap, 300)
+    car = BatchedCar()
+    car.setCarEdgeDistances(1080, -FOV / 2.0, FOV / 1080, 0.275)
+    n, steps = 65536, 50
+    rng = np.random.default_rng(42)
+    start = maps.sample_free_poses(dist, n, 404, colombia["resolution"], colombia["origin"], min_clear_px=6.0)
+    s0 = np.zeros((n, 11))
+    s0[:, :3] = start
+    s0[:, 3] = 2.0
+    actions = np.stack([rng.uniform(0, 7.0, (n, 5)), rng.uniform(-0.4189, 0.4189, (n, 5))], axis=2)
+    d_actions = torch.from_numpy(actions).cuda()
+    st = torch.from_numpy(s0.copy()).cuda()
+    out = car.rollout(rm, st, d_actions, steps, FOV)
+    idx = out["crash_index"].cpu().numpy()
+    assert np.all((idx == -(steps + 1)) | ((idx >= 0) & (idx < steps)))
+    st2 = torch.from_numpy(s0.copy()).cuda()
+    out2 = car.rollout(rm, st2, d_actions, steps, FOV)
+    assert torch.equal(out["crash_index"], out2["crash_index"]) and torch.equal(st, st2)
+    # subset against the oracle
+    p = orc.car_params()
+    edge = car.edge_distances()
+    m = orc.Marcher(dist, 300, colombia["resolution"], colombia["origin"])
+    sub = rng.choice(n, 48, replace=False)
+    agree = 0
+    for c in sub:
+        s = s0[c].copy()
+        poses = np.zeros((steps, 3), np.float32)
+        for i in range(steps):
+            orc.car_step(p, s, actions[c, i // 10, 0], actions[c, i // 10, 1], 0.01)
+            poses[i] = s[:3]
+        want = orc.car_is_crashed(m.calc_range_fan(poses, 1080, FOV), edge, 1080, steps, 0.001)
+        agree += int(want == idx[c])
+    assert agree >= 47
+    print(f"config 4: {np.mean(idx >= 0) * 100:.1f}% of cars crash within {steps} steps")
+
+
+def test_config5_large_map_reduced_pose_count(orc):
+    """8192^2 synthetic map (256 MiB fp32 field, not L2-resident); 270 beams."""
+    n = 8192
+    img = maps.synth_map(n, 5678)
+    grid = orc.mapserver_occupancy(img)
+    occ = orc.omap_from_grid(grid, True)
+    y = maps.synth_yaml(n)
+    omap = range_libc.PyOMap(maps.OccupancyGrid.make(grid.ravel(), n, n, y.resolution, y.origin))
+    d2 = orc.edt_exact(occ)
+    assert np.array_equal(omap.dist2(), d2)                      # exact integer EDT is the definition here
+    dist = orc.sqrt_dist2(d2)
+    assert np.array_equal(omap.dist(), dist)
+    differs = int((orc.edt_float(occ) != dist).sum())
+    print(f"8192^2: float-Felzenszwalb restatement differs from the exact EDT on {differs} cells")
+    rm = range_libc.PyRayMarchingGPU(omap, 300)
+    poses = maps.sample_free_poses(dist, 100_000, 505, y.resolution, y.origin)
+    out = np.zeros(100_000 * 270, np.float32)
+    rm.calc_range_fan(poses, out, FOV, 270)
+    want = orc.Marcher(dist, 300, y.resolution, y.origin).calc_range_fan(poses, 270, FOV, threads=0)
+    assert_ranges_match(out, want, y.resolution)

@@ -438,6 +438,51 @@ __global__ void __launch_bounds__(128) k_ray3(Args a, Lean q)
     a.outs[i] = __fmul_rn(r, P.w.scale);
 }
 
+// ---------------------------------------------------------------- V7: product loop + look-ahead touch when the
+// clearance is small (creeping rays pay one L2 round trip per 1-px step otherwise)
+template <int AHEAD, int MODE>
+__global__ void __launch_bounds__(128) k_touch(Args a, Lean q, float near)
+{
+    const unsigned i = blockIdx.x * 128u + threadIdx.x;
+    const unsigned total = (unsigned)a.num_poses * a.num_beams;
+    if (i >= total) return;
+    const MarchParams &P = a.P;
+    const unsigned k = __umulhi(i, q.magic) >> q.shift;
+    const int j = i - k * a.num_beams;
+    const float *p = a.poses + 3 * k;
+    const float thw = __ldg(p + 2);
+    const GridPose g = rl::world_to_grid(P.w, __ldg(p), __ldg(p + 1), thw);
+    const float thg = __fadd_rn(-__fadd_rn(thw, fmaf((float)j, q.inc, -0.5f * a.fov)), P.w.rotation_const);
+    float dx, dy;
+    rl::glibc_sincosf(thg, &dy, &dx);
+    const float x0 = g.y, y0 = g.x;
+    float t = 0.f, r = P.max_range;
+    if ((x0 == x0) && (y0 == y0) && (dx == dx)) {
+        while (t < P.max_range) {
+            const int px = __float2int_rz(fmaf(dx, t, x0)), py = __float2int_rz(fmaf(dy, t, y0));
+            if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) break;
+            const float *cell = P.dist + (px * P.cols + py);
+            const float d = __ldg(cell);
+            if (d <= 0.0f) {
+                const float xd = __fsub_rn((float)px, x0), yd = __fsub_rn((float)py, y0);
+                r = sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+                break;
+            }
+            if (d < near) {   // touch the sector AHEAD px further along the ray
+                const float ta = t + (float)AHEAD;
+                const int ax = __float2int_rz(fmaf(dx, ta, x0)), ay = __float2int_rz(fmaf(dy, ta, y0));
+                if ((unsigned)ax < (unsigned)P.rows && (unsigned)ay < (unsigned)P.cols) {
+                    const float *pa = P.dist + (ax * P.cols + ay);
+                    if (MODE == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(pa));
+                    else { float junk; asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(junk) : "l"(pa)); }
+                }
+            }
+            t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+        }
+    }
+    a.outs[i] = __fmul_rn(r, P.w.scale);
+}
+
 // ---------------------------------------------------------------- harness
 static std::vector<char> slurp(const std::string &path)
 {
@@ -572,6 +617,13 @@ int main(int argc, char **argv)
         R.run("ray3 opt3", [&] { k_ray3<3><<<b3, 128>>>(a, q); });
         R.run("ray3 opt7", [&] { k_ray3<7><<<b3, 128>>>(a, q); });
         R.run("ray3 opt5", [&] { k_ray3<5><<<b3, 128>>>(a, q); });
+        R.run("touch prefetch.L1 ahead4 near3", [&] { k_touch<4, 0><<<b3, 128>>>(a, q, 3.0f); });
+        R.run("touch ld ahead4 near3", [&] { k_touch<4, 1><<<b3, 128>>>(a, q, 3.0f); });
+        R.run("touch ld ahead3 near2", [&] { k_touch<3, 1><<<b3, 128>>>(a, q, 2.0f); });
+        R.run("touch ld ahead6 near3", [&] { k_touch<6, 1><<<b3, 128>>>(a, q, 3.0f); });
+        R.run("touch ld ahead4 near1.5", [&] { k_touch<4, 1><<<b3, 128>>>(a, q, 1.5f); });
+        R.run("touch ld ahead8 near4", [&] { k_touch<8, 1><<<b3, 128>>>(a, q, 4.0f); });
+        R.run("touch prefetch.L1 ahead8 near4", [&] { k_touch<8, 0><<<b3, 128>>>(a, q, 4.0f); });
         R.run("lean bs128 rpl1", [&] { k_lean<128, 1><<<nb(128, 1), 128>>>(a, q, 1 << 30); });
         R.run("lean bs256 rpl1", [&] { k_lean<256, 1><<<nb(256, 1), 256>>>(a, q, 1 << 30); });
         R.run("lean bs128 rpl2", [&] { k_lean<128, 2><<<nb(128, 2), 128>>>(a, q, 1 << 30); });
