@@ -66,10 +66,8 @@ typedef enum rl_status {
     RL_ERR_OOM = -4        /* host or device allocation failed                  */
 } rl_status;
 
-/* marcher flags */
+/* marcher flags (none defined yet: the only mode is the bit-exact one) */
 #define RL_FLAG_DEFAULT 0u
-#define RL_FLAG_TRIG_TABLE 1u /* fast mode: per-beam sin/cos by angle addition from a  */
-                              /* shared-memory table (not bit-identical to cosf/sinf)   */
 
 /* dist2 value of a cell from which no occupied cell is reachable (empty map) */
 #define RL_DIST2_INF 0x3fffffff

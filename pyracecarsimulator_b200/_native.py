@@ -19,7 +19,6 @@ RL_ERR_CUDA = -2
 RL_ERR_NO_DEVICE = -3
 RL_ERR_OOM = -4
 RL_FLAG_DEFAULT = 0
-RL_FLAG_TRIG_TABLE = 1
 RL_DIST2_INF = 0x3FFFFFFF
 
 

@@ -3,13 +3,15 @@
 // range_libc's PyOMap + DistanceTransform constructors (reference call sites
 // scripts/ros_interface.py:80-86, :210 and scripts/scan_simulator.py:72-76).
 //
-// Kernel pair (north_star (a)):
-//   edt_cols_kernel  one thread per map column: classifies every source cell through a
-//                    256-entry bit LUT (map_server thresholds / binarisation / `> 10` cut are
-//                    all pure functions of one byte, so the host folds them into the LUT with
-//                    the reference's double arithmetic), applies map_server's y-flip, writes
-//                    the occupancy byte and the distance g to the nearest occupied cell in
-//                    the same column (down sweep then up sweep), as saturating u16.
+// Kernels (north_star (a): column pass + row pass):
+//   edt_classify_kernel  one thread per (column, 64-row segment): classifies every source cell
+//                    through a 256-entry bit LUT (map_server thresholds / binarisation / `> 10`
+//                    cut are all pure functions of one byte, so the host folds them into the LUT
+//                    with the reference's double arithmetic), applies map_server's y-flip, writes
+//                    the occupancy byte, records the segment's first/last occupied row.
+//   edt_cols_kernel  same mapping: distance g to the nearest occupied cell in the same column
+//                    (down sweep seeded from the segments above, up sweep from those below), as
+//                    saturating u16.
 //   edt_rows_kernel  one CTA per map row with the row's g^2 staged in shared memory: each
 //                    thread takes the lower envelope min_k (k^2 + g^2[q +- k]) by an outward
 //                    scan that stops as soon as k^2 >= best, which is exact in integers and
@@ -34,52 +36,65 @@ __device__ __forceinline__ uint32_t lut_bit(const ByteLut &lut, uint32_t p)
     return (lut.w[p >> 5] >> (p & 31u)) & 1u;
 }
 
-constexpr int COLS_BATCH = 8;
+constexpr int SEG_ROWS = 64;   // rows per column segment: W * ceil(H/64) threads instead of W
+constexpr int SEG_NONE_LAST = -1;
+constexpr int SEG_NONE_FIRST = 0x3fffffff;
 
-__global__ void __launch_bounds__(32)
-edt_cols_kernel(const uint8_t *__restrict__ src, int rows, int cols, int flip, ByteLut lut,
-                uint8_t *__restrict__ occ, uint16_t *__restrict__ g)
+// Column pass, step 1: classify (byte LUT + map_server y-flip), write the occupancy byte, and record
+// for every (segment, column) the first and last occupied row inside the segment.
+__global__ void __launch_bounds__(128)
+edt_classify_kernel(const uint8_t *__restrict__ src, int rows, int cols, int flip, ByteLut lut,
+                    uint8_t *__restrict__ occ, int *__restrict__ seg_first, int *__restrict__ seg_last)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int seg = blockIdx.y;
     if (c >= cols) return;
-    uint32_t run = G_INF;
-    // down sweep, loads batched COLS_BATCH deep so they overlap (they do not depend on `run`)
-    for (int r0 = 0; r0 < rows; r0 += COLS_BATCH) {
-        uint32_t p[COLS_BATCH];
-#pragma unroll
-        for (int i = 0; i < COLS_BATCH; ++i) {
-            int r = r0 + i;
-            int sr = flip ? rows - 1 - r : r;
-            p[i] = (r < rows) ? src[(size_t)sr * cols + c] : 0u;
-        }
-#pragma unroll
-        for (int i = 0; i < COLS_BATCH; ++i) {
-            int r = r0 + i;
-            if (r < rows) {
-                uint32_t o = lut_bit(lut, p[i]);
-                run = o ? 0u : min(run + 1u, G_INF);
-                occ[(size_t)r * cols + c] = (uint8_t)o;
-                g[(size_t)r * cols + c] = (uint16_t)run;
-            }
-        }
+    const int r0 = seg * SEG_ROWS, r1 = min(rows, r0 + SEG_ROWS);
+    int first = SEG_NONE_FIRST, last = SEG_NONE_LAST;
+#pragma unroll 8
+    for (int r = r0; r < r1; ++r) {
+        const int sr = flip ? rows - 1 - r : r;
+        const uint32_t o = lut_bit(lut, src[(size_t)sr * cols + c]);
+        occ[(size_t)r * cols + c] = (uint8_t)o;
+        if (o) { first = min(first, r); last = r; }
     }
-    // up sweep
-    run = G_INF;
-    for (int r0 = rows - 1; r0 >= 0; r0 -= COLS_BATCH) {
-        uint32_t gv[COLS_BATCH];
-#pragma unroll
-        for (int i = 0; i < COLS_BATCH; ++i) {
-            int r = r0 - i;
-            gv[i] = (r >= 0) ? g[(size_t)r * cols + c] : 0u;
-        }
-#pragma unroll
-        for (int i = 0; i < COLS_BATCH; ++i) {
-            int r = r0 - i;
-            if (r >= 0) {
-                run = (gv[i] == 0u) ? 0u : min(run + 1u, G_INF);
-                if (run < gv[i]) g[(size_t)r * cols + c] = (uint16_t)run;
-            }
-        }
+    seg_first[(size_t)seg * cols + c] = first;
+    seg_last[(size_t)seg * cols + c] = last;
+}
+
+// Column pass, step 2: distance g (saturating u16) to the nearest occupied cell of the same column:
+// down sweep seeded with the last occupied row above the segment, up sweep seeded with the first
+// occupied row below it.
+__global__ void __launch_bounds__(128)
+edt_cols_kernel(const uint8_t *__restrict__ occ, int rows, int cols, int nseg,
+                const int *__restrict__ seg_first, const int *__restrict__ seg_last,
+                uint16_t *__restrict__ g)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int seg = blockIdx.y;
+    if (c >= cols) return;
+    const int r0 = seg * SEG_ROWS, r1 = min(rows, r0 + SEG_ROWS);
+    int above = SEG_NONE_LAST, below = SEG_NONE_FIRST;
+    for (int s2 = seg - 1; s2 >= 0; --s2) {
+        const int l = seg_last[(size_t)s2 * cols + c];
+        if (l != SEG_NONE_LAST) { above = l; break; }
+    }
+    for (int s2 = seg + 1; s2 < nseg; ++s2) {
+        const int f = seg_first[(size_t)s2 * cols + c];
+        if (f != SEG_NONE_FIRST) { below = f; break; }
+    }
+    uint32_t run = (above == SEG_NONE_LAST) ? G_INF : min((uint32_t)(r0 - 1 - above), G_INF);
+#pragma unroll 8
+    for (int r = r0; r < r1; ++r) {
+        run = occ[(size_t)r * cols + c] ? 0u : min(run + 1u, G_INF);
+        g[(size_t)r * cols + c] = (uint16_t)run;
+    }
+    run = (below == SEG_NONE_FIRST) ? G_INF : min((uint32_t)(below - r1), G_INF);
+#pragma unroll 8
+    for (int r = r1 - 1; r >= r0; --r) {
+        const uint32_t gv = g[(size_t)r * cols + c];
+        run = (gv == 0u) ? 0u : min(run + 1u, G_INF);
+        if (run < gv) g[(size_t)r * cols + c] = (uint16_t)run;
     }
 }
 
@@ -160,10 +175,13 @@ int32_t build_map(const uint8_t *src, int width, int height, int flip, const Byt
     const size_t n = (size_t)width * height;
     uint8_t *d_src = nullptr;
     uint16_t *d_g = nullptr;
+    int *d_seg = nullptr;
+    const int nseg = (height + SEG_ROWS - 1) / SEG_ROWS;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     auto cleanup = [&](bool all) {
         cudaFree(d_src);
         cudaFree(d_g);
+        cudaFree(d_seg);
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
         if (all) { cudaFree(m->d_occ); cudaFree(m->d_dist2); cudaFree(m->d_dist); delete m; }
@@ -179,6 +197,7 @@ int32_t build_map(const uint8_t *src, int width, int height, int flip, const Byt
     } while (0)
     RL_TRY(cudaMalloc(&d_src, n));
     RL_TRY(cudaMalloc(&d_g, n * sizeof(uint16_t)));
+    RL_TRY(cudaMalloc(&d_seg, (size_t)2 * nseg * width * sizeof(int)));
     RL_TRY(cudaMalloc(&m->d_occ, n));
     RL_TRY(cudaMalloc(&m->d_dist2, n * sizeof(int32_t)));
     RL_TRY(cudaMalloc(&m->d_dist, n * sizeof(float)));
@@ -188,7 +207,12 @@ int32_t build_map(const uint8_t *src, int width, int height, int flip, const Byt
     const size_t smem = (size_t)width * sizeof(uint32_t);
     RL_TRY(cudaFuncSetAttribute(edt_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RL_TRY(cudaEventRecord(e0, 0));
-    edt_cols_kernel<<<(width + 31) / 32, 32>>>(d_src, height, width, flip, lut, m->d_occ, d_g);
+    {
+        const dim3 grid((width + 127) / 128, nseg);
+        int *seg_first = d_seg, *seg_last = d_seg + (size_t)nseg * width;
+        edt_classify_kernel<<<grid, 128>>>(d_src, height, width, flip, lut, m->d_occ, seg_first, seg_last);
+        edt_cols_kernel<<<grid, 128>>>(m->d_occ, height, width, nseg, seg_first, seg_last, d_g);
+    }
     edt_rows_kernel<<<height, 256, smem>>>(d_g, height, width, m->d_dist2, m->d_dist);
     RL_TRY(cudaGetLastError());
     RL_TRY(cudaEventRecord(e1, 0));

@@ -86,3 +86,40 @@ def test_concurrent_callers_share_one_marcher(sim_env, colombia_scan):
     [t.start() for t in ts]
     [t.join() for t in ts]
     assert not errs, errs
+
+
+def test_racecar_simulator_facade(orc, sim_env, colombia_scan):
+    """RacecarSimulator (scripts/racecar_simulator_v2.py): runScan from the lidar pose, updatePose,
+    checkCollision / checkCollisionMany against the oracle car + marcher."""
+    from pyracecarsimulator_b200.racecar import DEFAULT_CAR_CONFIG
+    from pyracecarsimulator_b200.racecar_simulator import RacecarSimulator
+    omap, mrx, col, marcher = sim_env
+    cfg = dict(DEFAULT_CAR_CONFIG, scan_dist_to_base=0.275, batch_size=20, scan_beams=1080, scan_fov=4.71,
+               scan_std=0.01, scan_max_range=15.0, free_thresh=0.8)
+    rcs = RacecarSimulator(cfg)
+    rcs.setMap(omap, col["resolution"], col["origin"])
+    rcs.setRaytracingMethod("RMGPU")
+    assert rcs.scan_simulator.mrx == 300
+    # zero-state car: the lidar sits at (0.275, 0, 0)  (BASELINE config 1)
+    rcs.runScan()
+    assert_ranges_match(rcs.getScan(), colombia_scan["fan"][:1080], 0.05)
+    assert rcs.checkCollision() == -2                     # one pose, no crash
+    # drive: state follows the oracle
+    p = orc.car_params()
+    want = np.zeros(11)
+    rcs.drive(2.0, 0.2)
+    for _ in range(30):
+        rcs.updatePose()
+        orc.car_step(p, want, 2.0, 0.2, 0.01)
+    got = rcs.getState()
+    assert np.allclose(got, want, rtol=1e-11, atol=1e-13)
+    assert rcs.getTravelDistance() == pytest.approx(want[8], rel=1e-11)
+    assert rcs.getMeanVelocity() == pytest.approx(want[9] / want[10], rel=1e-11)
+    # checkCollisionMany == scanMany + isCrashed
+    poses = maps.sample_free_poses(orc.edt_float(colombia_scan["occ"]), 20, 321, col["resolution"], col["origin"],
+                                   min_clear_px=1.0)
+    edge = orc.car_edge_distances(p, 1080, -4.71 / 2.0, 4.71 / 1080, 0.275)
+    want_idx = orc.car_is_crashed(marcher.calc_range_fan(poses, 1080, 4.71), edge, 1080, 20, 0.001)
+    assert rcs.checkCollisionMany(poses) == want_idx
+    rcs.stop()
+    assert not rcs.getState().any()
