@@ -248,6 +248,20 @@ def run_native(args, rank, world, local_rank):
             raise SystemExit("bench.py: fused p2p gather differs from march + NCCL all_gather")
     launches = K  # one march kernel per step (flush fills and NCCL kernels are not ours)
 
+    # ---- N>1: the same steps with the ranges left sharded (no exchange), for the record ----
+    nogather_ms = 0.0
+    if dist_on:
+        evn = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        barrier()
+        for i in range(K):
+            if flush is not None:
+                flush.fill_(i & 0xFF)
+            evn[i][0].record()
+            rm.calc_range_fan(d_poses[i % n_sets], d_out, FOV, B)
+            evn[i][1].record()
+        barrier()
+        nogather_ms = sum(a.elapsed_time(b) for a, b in evn)
+
     # ---- e2e through the reference-facing API with host buffers ----
     sim = ScanSimulator2D(B, FOV, 0.01, batch_size=P)
     sim.setMap(omap, MAX_RANGE_PX, y.resolution, y.origin)
@@ -266,10 +280,20 @@ def run_native(args, rank, world, local_rank):
     clocks = sampler.result()
 
     # ---- max over ranks ----
-    t = torch.tensor([dev_ms, e2e_s, t_wall], dtype=torch.float64, device=dev)
+    # PCIe ceiling of the e2e path: pinned D2H of one step's ranges
+    h_pin = torch.empty(n_rays, dtype=torch.float32, pin_memory=True)
+    h_pin.copy_(d_out, non_blocking=True)
+    torch.cuda.synchronize()
+    tp = time.perf_counter()
+    for _ in range(5):
+        h_pin.copy_(d_out, non_blocking=True)
+    torch.cuda.synchronize()
+    d2h_gbs = 5 * n_rays * 4 / (time.perf_counter() - tp) / 1e9
+
+    t = torch.tensor([dev_ms, e2e_s, t_wall, nogather_ms], dtype=torch.float64, device=dev)
     if dist_on:
         tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
-    dev_ms, e2e_s, t_wall = (float(v) for v in t.tolist())
+    dev_ms, e2e_s, t_wall, nogather_ms = (float(v) for v in t.tolist())
 
     if rank == 0:
         # ---- roofline inputs: algorithmic bytes of ONE launch (4 B/step + 4 B/ray + 12 B/pose) ----
@@ -357,14 +381,20 @@ def run_native(args, rank, world, local_rank):
                                        "(fused all-gather) + 4-byte all_reduce as barrier, inside the step" if peer is not None else ""),
                        "l2": "no flush" if args.no_flush else "flushed between steps (256 MiB fill), fill excluded from the per-step events",
                        "timing": "CUDA events per step on the launching stream, summed, max over ranks",
-                       "trig": "exact (sincosf per beam)"},
+                       "trig": "exact: glibc's sinf/cosf algorithm evaluated per beam on the device (bit parity with the host libm)"},
             "wall_ms_per_step_incl_flush": t_wall / K * 1e3,
             "e2e": {"value": total_rays * e2e_steps / e2e_s, "unit": "rays/s",
                     "h2d_bytes_per_step": P * 12, "d2h_bytes_per_step": n_rays * 4, "steps": e2e_steps,
-                    "api": "ScanSimulator2D.scanMany(host poses) -> host ranges (pinned), per rank"},
+                    "api": "ScanSimulator2D.scanMany(host poses) -> host ranges (pinned), per rank",
+                    "pinned_d2h_gbs": d2h_gbs,
+                    "pcie_bound_rays_per_s": world * d2h_gbs * 1e9 / 4.0},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "ingest_ms": omap.ingest_ms,
         }
+        if dist_on:
+            line["sharded_no_gather"] = {"value": total_rays * K / (nogather_ms * 1e-3), "unit": "rays/s",
+                                         "ms_per_step": nogather_ms / K,
+                                         "note": "same steps with the ranges left on their GPUs (no exchange)"}
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))
