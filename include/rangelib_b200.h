@@ -197,6 +197,13 @@ RL_API int32_t rl_rollout(rl_marcher *m, rl_car *car, double *d_states, const do
                           int32_t *d_crash_index, double *d_reward, float *d_poses, double *d_vsum,
                           void *stream);
 
+/* FollowGap(ws, max_distance, max_angle, angle_inc).eval(scan, num_rays) for `num_scans` scans at */
+/* once (followgap/followgap.hpp:104-129; caller scripts/mcts.py:262-267): d_scans is             */
+/* (num_scans, num_rays) fp32 ranges in metres, d_out[s] the steering angle.  num_rays >= 10.      */
+RL_API int32_t rl_follow_gap(const float *d_scans, int64_t num_scans, int32_t num_rays,
+                             float max_distance, float max_angle, float angle_inc, float *d_out,
+                             void *stream);
+
 /* ---- measurement support (not on the product path) ---- */
 /* Throughput, in GB/s at 4 bytes per gather, of independent random 4-byte gathers from a    */
 /* `buffer_bytes` L2-resident buffer: the denominator of the L2-gather roofline.             */

@@ -29,11 +29,13 @@ i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 def build(force=False):
     """Compile liboracle.so (and _ref/ when /root/reference is present)."""
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("rangelib_oracle.c", "car_oracle.c", "trig_twin.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("rangelib_oracle.c", "car_oracle.c", "trig_twin.c", "followgap_oracle.c")]
     stale = force or not os.path.exists(so) or any(
         os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     ref_so = os.path.join(_HERE, "_ref", "libracecar_ref.so")
-    want_ref = os.path.exists("/root/reference/racecar/src/racecar.cpp") and not os.path.exists(ref_so)
+    fg_so = os.path.join(_HERE, "_ref", "libfollowgap_ref.so")
+    want_ref = os.path.exists("/root/reference/racecar/src/racecar.cpp") and not (
+        os.path.exists(ref_so) and os.path.exists(fg_so))
     if stale or want_ref:
         env = dict(os.environ)
         env.pop("CC", None)
@@ -85,6 +87,8 @@ def lib():
     L.orc_twin_sincosf.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.orc_twin_mismatches.restype = C.c_uint64
     L.orc_twin_mismatches.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64]
+    L.orc_followgap_eval.restype = C.c_float
+    L.orc_followgap_eval.argtypes = [f32p, C.c_int, C.c_float, C.c_float, C.c_float]
     L.orc_car_step.argtypes = [C.POINTER(CarParams), f64p, C.c_double, C.c_double, C.c_double]
     L.orc_car_scan_pose.argtypes = [f64p, C.c_double, f64p]
     L.orc_car_edge_distances.argtypes = [C.POINTER(CarParams), C.c_int, C.c_double, C.c_double,
@@ -233,6 +237,32 @@ def car_edge_distances(params, num_rays, min_ang, inc, scan_dist_to_base):
 def car_is_crashed(rays, edge, num_rays, poses, crash_thresh):
     rays = np.ascontiguousarray(rays, dtype=np.float32)
     return int(lib().orc_car_is_crashed(rays, edge, num_rays, poses, crash_thresh))
+
+
+def followgap_eval(lidar, max_distance=15.0, max_angle=0.4189, angle_inc=0.004):
+    """FollowGap(ws, md, ma, inc).eval(lidar, len(lidar)) restated (window size is unused upstream)."""
+    lidar = np.ascontiguousarray(lidar, dtype=np.float32)
+    return float(lib().orc_followgap_eval(lidar, lidar.size, max_distance, max_angle, angle_inc))
+
+
+_FG = None
+
+
+def ref_followgap_eval(lidar, ws=10, max_distance=15.0, max_angle=0.4189, angle_inc=0.004):
+    """The unmodified reference FollowGap (followgap/followgap.hpp) via ref_followgap_shim.cpp."""
+    global _FG
+    if _FG is None:
+        build()
+        _FG = C.CDLL(os.path.join(_HERE, "_ref", "libfollowgap_ref.so"))
+        _FG.ref_followgap_eval.restype = C.c_float
+        _FG.ref_followgap_eval.argtypes = [f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]
+    lidar = np.ascontiguousarray(lidar, dtype=np.float32).copy()
+    return float(_FG.ref_followgap_eval(lidar, lidar.size, ws, max_distance, max_angle, angle_inc))
+
+
+def followgap_ref_available():
+    build()
+    return os.path.exists(os.path.join(_HERE, "_ref", "libfollowgap_ref.so"))
 
 
 # --------------------------------------------------------------------------- the real reference
