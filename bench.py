@@ -7,8 +7,11 @@ A step is one pass of the hot path (the fork's 4-arg calc_range_many fan: scanMa
 batch of synthetic poses.  At N=1 the workload is BASELINE.json configs[1]: 4096 poses x 1080
 beams (fov 4.71, max range 300 px) on the 2049^2 stand-in for the missing maps/map.pgm
 (synth_map(2049, 1234)).  For N>1 every rank marches its own 4096-pose
-shard against its own replica of the map (weak scaling) and the ranges are all-gathered over
-NCCL (--gather none to leave them sharded).
+shard against its own replica of the map (weak scaling; rays are independent, so the path has no
+exchange step and `value` times the sharded march).  The optional delivery of all ranges to every
+GPU -- north_star's "final gather of ranges over NVLink" -- is timed in the same run and reported
+under `gather` (fused: the march kernel stores into every GPU's buffer over NVLink peer memory)
+and `gather_nccl` (march + NCCL all_gather); `--gather p2p|allgather` puts it inside `value`.
 
 One JSON line is printed by rank 0; keys follow the driver contract plus `roofline` and
 `cpu_baseline`.  `value` is device time (CUDA events per step on the launching stream, L2
@@ -43,9 +46,10 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--poses", type=int, default=4096, help="poses per GPU per step")
     ap.add_argument("--beams", type=int, default=1080)
-    ap.add_argument("--gather", default="p2p", choices=["p2p", "allgather", "none"],
-                    help="N>1: p2p = march kernel stores into every GPU's gathered buffer over NVLink (fused); "
-                         "allgather = march then NCCL all_gather; none = ranges stay sharded")
+    ap.add_argument("--gather", default="none", choices=["p2p", "allgather", "none"],
+                    help="N>1, what `value` times: none = ranges stay sharded (default); p2p = march kernel stores into "
+                         "every GPU's gathered buffer over NVLink (fused); allgather = march then NCCL all_gather. "
+                         "The other variants are still measured and reported under `gather` / `gather_nccl`.")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps")
     return ap.parse_args()
@@ -199,34 +203,46 @@ def run_native(args, rank, world, local_rank):
                  for s in range(n_sets)]
     d_poses = [torch.from_numpy(p).to(dev) for p in pose_sets]
     d_out = torch.empty(n_rays, dtype=torch.float32, device=dev)
-    d_all = torch.empty(world * n_rays, dtype=torch.float32, device=dev) if dist_on and args.gather == "allgather" else None
+    d_all = torch.empty(world * n_rays, dtype=torch.float32, device=dev) if dist_on else None
     rm = range_libc.PyRayMarchingGPU(omap, MAX_RANGE_PX)
     peer = None
-    if dist_on and args.gather == "p2p":
+    if dist_on:
         from pyracecarsimulator_b200.sharded import PeerGather
         peer = PeerGather(local_rank, n_rays)
         stream_ptr = int(torch.cuda.current_stream(local_rank).cuda_stream)
+    mode = args.gather if dist_on else "none"
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def step(i, ev0=None, ev1=None):
+    def step(i, ev0=None, ev1=None, how=None):
+        how = mode if how is None else how
         if flush is not None:
             flush.fill_(i & 0xFF)          # 256 MiB write > 126 MB L2: evicts the distance field
         if ev0 is not None:
             ev0.record()
-        if peer is not None:
+        if how == "p2p":
             peer.march(rm, d_poses[i % n_sets], FOV, B, stream_ptr)   # fused march + all-gather
             peer.sync()
         else:
             rm.calc_range_fan(d_poses[i % n_sets], d_out, FOV, B)
-            if d_all is not None:
+            if how == "allgather":
                 tdist.all_gather_into_tensor(d_all, d_out)
         if ev1 is not None:
             ev1.record()
 
+    def timed(how):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        for i in range(3):
+            step(i, how=how)
+        barrier()
+        for i in range(K):
+            step(i, *evs[i], how=how)
+        barrier()
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    K = args.steps
     for i in range(args.warmup):
         step(i)
     barrier()
-    K = args.steps
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -248,19 +264,11 @@ def run_native(args, rank, world, local_rank):
             raise SystemExit("bench.py: fused p2p gather differs from march + NCCL all_gather")
     launches = K  # one march kernel per step (flush fills and NCCL kernels are not ours)
 
-    # ---- N>1: the same steps with the ranges left sharded (no exchange), for the record ----
-    nogather_ms = 0.0
+    # ---- N>1: the variants `value` does not time, same K steps each ----
+    other_ms = {}
     if dist_on:
-        evn = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-        barrier()
-        for i in range(K):
-            if flush is not None:
-                flush.fill_(i & 0xFF)
-            evn[i][0].record()
-            rm.calc_range_fan(d_poses[i % n_sets], d_out, FOV, B)
-            evn[i][1].record()
-        barrier()
-        nogather_ms = sum(a.elapsed_time(b) for a, b in evn)
+        for how in ("none", "p2p", "allgather"):
+            other_ms[how] = dev_ms if how == mode else timed(how)
 
     # ---- e2e through the reference-facing API with host buffers ----
     sim = ScanSimulator2D(B, FOV, 0.01, batch_size=P)
@@ -290,10 +298,11 @@ def run_native(args, rank, world, local_rank):
     torch.cuda.synchronize()
     d2h_gbs = 5 * n_rays * 4 / (time.perf_counter() - tp) / 1e9
 
-    t = torch.tensor([dev_ms, e2e_s, t_wall, nogather_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_s, t_wall] + [other_ms.get(h, 0.0) for h in ("none", "p2p", "allgather")],
+                     dtype=torch.float64, device=dev)
     if dist_on:
         tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
-    dev_ms, e2e_s, t_wall, nogather_ms = (float(v) for v in t.tolist())
+    dev_ms, e2e_s, t_wall, ms_none, ms_p2p, ms_nccl = (float(v) for v in t.tolist())
 
     if rank == 0:
         # ---- roofline inputs: algorithmic bytes of ONE launch (4 B/step + 4 B/ray + 12 B/pose) ----
@@ -376,9 +385,10 @@ def run_native(args, rank, world, local_rank):
                        "global_rays_per_step": total_rays, "map": f"{MAP_N}x{MAP_N} fp32 distance field "
                        f"({dist_field.nbytes >> 20} MiB, replicated per GPU)",
                        "parallelism": f"pose-sharded x{world}, map replicated" +
-                                      (", NCCL all_gather of ranges inside the step" if d_all is not None else "") +
-                                      (", ranges stored into every GPU's gathered buffer over NVLink by the march kernel "
-                                       "(fused all-gather) + 4-byte all_reduce as barrier, inside the step" if peer is not None else ""),
+                                      {"none": ", no exchange step (rays are independent)" if dist_on else "",
+                                       "allgather": ", NCCL all_gather of ranges inside the step",
+                                       "p2p": ", ranges stored into every GPU's gathered buffer over NVLink by the march "
+                                              "kernel (fused all-gather) + 4-byte all_reduce as barrier, inside the step"}[mode],
                        "l2": "no flush" if args.no_flush else "flushed between steps (256 MiB fill), fill excluded from the per-step events",
                        "timing": "CUDA events per step on the launching stream, summed, max over ranks",
                        "trig": "exact: glibc's sinf/cosf algorithm evaluated per beam on the device (bit parity with the host libm)"},
@@ -392,9 +402,13 @@ def run_native(args, rank, world, local_rank):
             "ingest_ms": omap.ingest_ms,
         }
         if dist_on:
-            line["sharded_no_gather"] = {"value": total_rays * K / (nogather_ms * 1e-3), "unit": "rays/s",
-                                         "ms_per_step": nogather_ms / K,
-                                         "note": "same steps with the ranges left on their GPUs (no exchange)"}
+            def entry(ms, note):
+                return {"value": total_rays * K / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms / K, "note": note}
+            line["sharded"] = entry(ms_none, "ranges left on their GPUs: no exchange step")
+            line["gather"] = entry(ms_p2p, "fused: the march kernel stores every range into all GPUs' gathered buffers over "
+                                           "NVLink peer memory (rl_calc_range_fan_allgather), 4-byte all_reduce as barrier; "
+                                           f"every GPU receives {(world - 1) * n_rays * 4 / 1e6:.0f} MB per step")
+            line["gather_nccl"] = entry(ms_nccl, "march, then NCCL all_gather_into_tensor of the ranges")
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))

@@ -83,10 +83,14 @@ RL_API int32_t rl_device_count(int32_t *count);
 /* ---- map ingest (GPU: threshold -> occupancy -> exact integer squared EDT -> sqrt) ---- */
 
 /* From image pixels as stored in the PGM (rows top to bottom, `width` columns), applying  */
-/* map_server's trinary thresholds and y-flip, then (binarise != 0) the reference's        */
-/* `>0 -> 255 else 0` (scripts/ros_interface.py:80-86), then PyOMap's `> 10` cut.          */
+/* map_server's thresholds (mode: trinary is what every shipped map.yaml uses) and y-flip,  */
+/* then (binarise != 0) the reference's `>0 -> 255 else 0` (scripts/ros_interface.py:80-86), */
+/* then PyOMap's `> 10` cut.                                                               */
+#define RL_MAP_TRINARY 0
+#define RL_MAP_SCALE 1
+#define RL_MAP_RAW 2
 RL_API int32_t rl_map_from_image(const uint8_t *pixels, int32_t width, int32_t height, int32_t negate,
-                          double occupied_thresh, double free_thresh, int32_t binarise,
+                          double occupied_thresh, double free_thresh, int32_t mode, int32_t binarise,
                           double resolution, double origin_x, double origin_y, double origin_yaw,
                           int32_t device, rl_map **out);
 

@@ -68,6 +68,7 @@ def lib():
         return _LIB
     L = C.CDLL(build())
     L.orc_mapserver_occupancy.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, i8p]
+    L.orc_mapserver_occupancy_mode.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, i8p]
     L.orc_omap_from_grid.argtypes = [i8p, C.c_int64, C.c_int, u8p]
     L.orc_edt_float.argtypes = [u8p, C.c_int, C.c_int, f32p, C.c_void_p]
     L.orc_edt_exact.argtypes = [u8p, C.c_int, C.c_int, i32p]
@@ -100,13 +101,19 @@ def lib():
 
 
 # --------------------------------------------------------------------------- map ingest
-def mapserver_occupancy(img, negate=0, occupied_thresh=0.65, free_thresh=0.196):
+MODES = {"trinary": 0, "scale": 1, "raw": 2}
+
+
+def mapserver_occupancy(img, negate=0, occupied_thresh=0.65, free_thresh=0.196, mode="trinary"):
     """(H, W) uint8 image rows top-to-bottom -> (H, W) int8 OccupancyGrid, row 0 = bottom."""
     img = np.ascontiguousarray(img, dtype=np.uint8)
     h, w = img.shape
     out = np.empty((h, w), dtype=np.int8)
-    lib().orc_mapserver_occupancy(img, w, h, int(negate), float(occupied_thresh),
-                                  float(free_thresh), out)
+    if mode == "trinary":
+        lib().orc_mapserver_occupancy(img, w, h, int(negate), float(occupied_thresh), float(free_thresh), out)
+    else:
+        lib().orc_mapserver_occupancy_mode(img, w, h, int(negate), float(occupied_thresh), float(free_thresh),
+                                           MODES[mode], out)
     return out
 
 

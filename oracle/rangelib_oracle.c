@@ -45,9 +45,34 @@
 #define ORC_EXPORT __attribute__((visibility("default")))
 
 /* ------------------------------------------------------------------------- */
-/* A.1  PGM pixel -> map_server OccupancyGrid cell (trinary mode), y-flipped. */
-/* maps/map.yaml:1-6 supplies negate / occupied_thresh / free_thresh.         */
+/* A.1  PGM pixel -> map_server OccupancyGrid cell, y-flipped.                 */
+/* maps/map.yaml:1-6 supplies negate / occupied_thresh / free_thresh; every   */
+/* shipped yaml uses the default trinary mode (mode 0).  Modes 1 (scale) and  */
+/* 2 (raw) restate ROS1 map_server's image_loader for 8-bit grey images       */
+/* (not exercised by the reference's own maps).          */
 /* ------------------------------------------------------------------------- */
+static int8_t mapserver_cell(int p, int negate, double occupied_thresh, double free_thresh, int mode)
+{
+    if (mode == 2) return (int8_t)(unsigned char)p;            /* raw: the pixel value itself */
+    double shade = negate ? p / 255.0 : (255 - p) / 255.0;
+    if (shade > occupied_thresh) return 100;
+    if (shade < free_thresh) return 0;
+    if (mode == 0) return -1;                                   /* trinary: unknown */
+    double ratio = (shade - free_thresh) / (occupied_thresh - free_thresh);
+    return (int8_t)(unsigned char)(1 + 98 * ratio);             /* scale */
+}
+
+ORC_EXPORT void orc_mapserver_occupancy_mode(const uint8_t *img, int img_w, int img_h, int negate,
+                                             double occupied_thresh, double free_thresh, int mode,
+                                             int8_t *grid)
+{
+    for (int j = 0; j < img_h; ++j) {
+        int8_t *dst = grid + (size_t)(img_h - 1 - j) * img_w;
+        const uint8_t *src = img + (size_t)j * img_w;
+        for (int i = 0; i < img_w; ++i) dst[i] = mapserver_cell(src[i], negate, occupied_thresh, free_thresh, mode);
+    }
+}
+
 ORC_EXPORT void orc_mapserver_occupancy(const uint8_t *img, int img_w, int img_h,
                                         int negate, double occupied_thresh,
                                         double free_thresh, int8_t *grid)

@@ -243,18 +243,24 @@ void rl_map_release(const rl_map *cm)
 extern "C" {
 
 int32_t rl_map_from_image(const uint8_t *pixels, int32_t width, int32_t height, int32_t negate,
-                          double occupied_thresh, double free_thresh, int32_t binarise,
+                          double occupied_thresh, double free_thresh, int32_t mode, int32_t binarise,
                           double resolution, double origin_x, double origin_y, double origin_yaw,
                           int32_t device, rl_map **out)
 {
-    // map_server trinary rule per byte value, in double like map_server, then the reference's
-    // binarisation and PyOMap's cut.
+    // map_server's rule per byte value (trinary / scale / raw), in double like map_server, then the
+    // reference's binarisation and PyOMap's cut: all functions of one byte.
+    if (mode < RL_MAP_TRINARY || mode > RL_MAP_RAW) return rl::fail(RL_ERR_BAD_ARG, "rl_map_from_image: unknown mode");
     ByteLut lut{};
     for (int p = 0; p < 256; ++p) {
-        double shade = negate ? p / 255.0 : (255 - p) / 255.0;
-        int v = -1;
-        if (shade > occupied_thresh) v = 100;
-        else if (shade < free_thresh) v = 0;
+        int v;
+        if (mode == RL_MAP_RAW) v = (int8_t)(unsigned char)p;
+        else {
+            double shade = negate ? p / 255.0 : (255 - p) / 255.0;
+            if (shade > occupied_thresh) v = 100;
+            else if (shade < free_thresh) v = 0;
+            else if (mode == RL_MAP_TRINARY) v = -1;
+            else v = (int8_t)(unsigned char)(1 + 98 * ((shade - free_thresh) / (occupied_thresh - free_thresh)));
+        }
         if (binarise) v = (v > 0) ? 255 : 0;
         if (v > 10) lut.w[p >> 5] |= 1u << (p & 31);
     }

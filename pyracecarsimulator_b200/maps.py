@@ -117,6 +117,7 @@ class MapYaml:
     negate: int = 0
     occupied_thresh: float = 0.65
     free_thresh: float = 0.196
+    mode: str = "trinary"
 
 
 def load_map_yaml(path: str) -> MapYaml:
@@ -128,7 +129,7 @@ def load_map_yaml(path: str) -> MapYaml:
         image = os.path.join(os.path.dirname(os.path.abspath(path)), image)
     return MapYaml(image, float(y["resolution"]), tuple(float(v) for v in y["origin"]),
                    int(y.get("negate", 0)), float(y.get("occupied_thresh", 0.65)),
-                   float(y.get("free_thresh", 0.196)))
+                   float(y.get("free_thresh", 0.196)), str(y.get("mode", "trinary")))
 
 
 # --------------------------------------------------------------------------- synthetic maps

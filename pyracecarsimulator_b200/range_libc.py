@@ -20,6 +20,9 @@ from . import _native
 from .maps import MapYaml, load_map_yaml, quaternion_to_yaw, read_pgm
 
 
+MAP_MODES = {"trinary": 0, "scale": 1, "raw": 2}
+
+
 def _is_torch(a) -> bool:
     return type(a).__module__.split(".")[0] == "torch"
 
@@ -91,7 +94,7 @@ class PyOMap:
             img = read_pgm(y.image)
             self._meta = (y.resolution, y.origin[0], y.origin[1], y.origin[2])
             rc = L.rl_map_from_image(img.ctypes.data, img.shape[1], img.shape[0], y.negate,
-                                     y.occupied_thresh, y.free_thresh, int(bool(binarise)),
+                                     y.occupied_thresh, y.free_thresh, MAP_MODES[y.mode], int(bool(binarise)),
                                      y.resolution, y.origin[0], y.origin[1], y.origin[2],
                                      self.device, C.byref(h))
         elif isinstance(arg, np.ndarray):

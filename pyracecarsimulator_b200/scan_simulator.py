@@ -88,6 +88,11 @@ class ScanSimulator2D:
     def updateMap(self, ros_map):
         self.ros_map = ros_map
 
+    def laser_scan_metadata(self, scan_max_range=None):
+        """The LaserScan fields the reference publishes with every scan (scripts/ros_interface.py:342-345)."""
+        return dict(angle_min=-self.fov / 2.0, angle_max=self.fov / 2.0, angle_increment=self.fov / self.num_rays,
+                    range_max=scan_max_range if scan_max_range is not None else self.mrx * self.res)
+
     def scan(self, x, y, theta):
         if not self.hasMap or self.scan_method is None:
             raise RuntimeError("Doing a scan without a defined map / ray tracing method")

@@ -88,11 +88,14 @@ class PeerGather:
         dist.all_reduce(self._flag, group=self.group)
 
     def close(self):
+        """Collective: unmap every peer buffer on every rank before any rank frees its own."""
         L = self._native.lib()
+        torch.cuda.synchronize(self.device_index)
         dist.barrier(group=self.group)
         for p in self._opened:
             L.rl_peer_close(self.device_index, p)
         self._opened = []
+        dist.barrier(group=self.group)
         if self._own is not None:
             self._view = None
             L.rl_peer_free(self.device_index, self._own)

@@ -101,3 +101,20 @@ def test_bad_arguments_raise():
         range_libc.PyOMap(np.zeros((2, 20000), bool))   # wider than the supported 16384
     with pytest.raises(ValueError):
         range_libc.PyOMap(42)
+
+
+@pytest.mark.parametrize("mode,negate", [("trinary", 1), ("scale", 0), ("scale", 1), ("raw", 0)])
+def test_map_server_modes(orc, tmp_path, mode, negate):
+    """map_server `negate` and `mode: scale / raw`: still one byte LUT on the GPU."""
+    rng = np.random.default_rng(9)
+    img = rng.integers(0, 256, (90, 130), dtype=np.uint8)
+    img[20:30, 40:90] = 3
+    path = str(tmp_path / "m.pgm")
+    maps.write_pgm(path, img)
+    y = maps.MapYaml(path, 0.05, (0.0, 0.0, 0.0), negate, 0.65, 0.196, mode)
+    for binarise in (True, False):
+        omap = range_libc.PyOMap(y, binarise=binarise)
+        grid = orc.mapserver_occupancy(img, negate, 0.65, 0.196, mode)
+        occ = orc.omap_from_grid(grid, binarise)
+        assert np.array_equal(omap.occupancy(), occ)
+        assert np.array_equal(omap.dist2(), orc.edt_exact(occ))
