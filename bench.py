@@ -406,7 +406,11 @@ def run_native(args, rank, world, local_rank):
                 return {"value": total_rays * K / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms / K, "note": note}
             line["sharded"] = entry(ms_none, "ranges left on their GPUs: no exchange step")
             line["gather"] = entry(ms_p2p, "fused: the march kernel stores every range into all GPUs' gathered buffers over "
-                                           "NVLink peer memory (rl_calc_range_fan_allgather), 4-byte all_reduce as barrier; "
+                                           "NVLink peer memory (rl_calc_range_fan_allgather; backend " + peer.backend +
+                                           (", one multimem.st per range replicated by the NVSwitch" if peer.multicast else
+                                            ", one store per peer") + (f" [symmetric memory unavailable: {getattr(peer, '_symm_error', '')[:200]}]"
+                                                                      if peer.backend == "ipc" else "") +
+                                           "), barrier after the kernel; "
                                            f"every GPU receives {(world - 1) * n_rays * 4 / 1e6:.0f} MB per step")
             line["gather_nccl"] = entry(ms_nccl, "march, then NCCL all_gather_into_tensor of the ranges")
         if cpu_baseline is not None:

@@ -151,11 +151,14 @@ RL_API int32_t rl_peer_free(int32_t device, void *d_ptr);
 /* rl_calc_range_fan with the all-gather fused in: every range is stored straight into slot      */
 /* `rank` (offset rank*slot_rays) of each of the `world` gathered buffers peer_bufs[0..world)     */
 /* (peer_bufs is a HOST array of device pointers as mapped in this process).  Ranks synchronise  */
-/* afterwards with any stream-ordered collective before reading.                                 */
+/* afterwards with any stream-ordered collective before reading.  With RL_GATHER_MULTICAST      */
+/* peer_bufs[0] is an NVLS multicast address bound to all `world` buffers: one multimem.st per    */
+/* range, replicated by the NVSwitch.                                                            */
+#define RL_GATHER_MULTICAST 1u
 RL_API int32_t rl_calc_range_fan_allgather(rl_marcher *m, const float *d_poses, int64_t pose_stride_rows,
                                            void *const *peer_bufs, int32_t world, int32_t rank,
                                            int64_t slot_rays, int64_t num_poses, int32_t num_rays,
-                                           float fov, void *stream);
+                                           float fov, uint32_t flags, void *stream);
 
 /* Number of distance-field loads ("march steps") the last *_host call performed, when the */
 /* marcher was asked to count them (rl_marcher_count_steps(m, 1)); used by the roofline.    */

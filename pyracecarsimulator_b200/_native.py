@@ -61,7 +61,7 @@ SIGNATURES = {
     "rl_peer_open": (_i32, [_i32, _vp, C.POINTER(_vp)]),
     "rl_peer_close": (_i32, [_i32, _vp]),
     "rl_peer_free": (_i32, [_i32, _vp]),
-    "rl_calc_range_fan_allgather": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _i64, _i64, _i32, _f, _vp]),
+    "rl_calc_range_fan_allgather": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _i64, _i64, _i32, _f, C.c_uint32, _vp]),
     "rl_marcher_count_steps": (_i32, [_vp, _i32]),
     "rl_marcher_last_steps": (_i32, [_vp, C.POINTER(C.c_uint64)]),
     "rl_car_create": (_i32, [_vp, _i32, C.POINTER(_vp)]),

@@ -55,6 +55,7 @@ constexpr int MAX_PEERS = 16;
 struct PeerOut {
     float *buf[MAX_PEERS];   // gathered buffer of each rank (peer-mapped device pointers)
     int world;
+    int multicast;           // buf[0] is an NVLS multicast address: one multimem.st reaches every GPU
     int64_t offset;          // this rank's slot: rank * slot_rays
 };
 
@@ -88,8 +89,13 @@ march_pose_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_s
         rl::glibc_sincosf(thg, &s, &c);
         const float r = __fmul_rn(rl::march_ray<COUNT>(P, g.y, g.x, c, s, steps), P.w.scale);
         if (PEERS) {
+            if (peers.multicast) {   // the NVSwitch replicates the store to all GPUs of the multicast group
+                asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(peers.buf[0] + peers.offset + i), "f"(r)
+                             : "memory");
+            } else {
 #pragma unroll 1
-            for (int q = 0; q < peers.world; ++q) peers.buf[q][peers.offset + i] = r;
+                for (int q = 0; q < peers.world; ++q) peers.buf[q][peers.offset + i] = r;
+            }
         } else {
             outs[i] = r;
         }
@@ -411,7 +417,8 @@ int32_t rl_peer_free(int32_t device, void *d_ptr)
 // stream-ordered collective, e.g. a barrier) before anyone reads the gathered ranges.
 int32_t rl_calc_range_fan_allgather(rl_marcher *m, const float *d_poses, int64_t pose_stride_rows,
                                     void *const *peer_bufs, int32_t world, int32_t rank, int64_t slot_rays,
-                                    int64_t num_poses, int32_t num_rays, float fov, void *stream)
+                                    int64_t num_poses, int32_t num_rays, float fov, uint32_t flags,
+                                    void *stream)
 {
     if (!m || !peer_bufs || world < 1 || world > MAX_PEERS || rank < 0 || rank >= world || num_poses < 0 ||
         num_rays <= 0 || pose_stride_rows < 1 || num_poses * num_rays > slot_rays || (num_poses > 0 && !d_poses))
@@ -424,6 +431,7 @@ int32_t rl_calc_range_fan_allgather(rl_marcher *m, const float *d_poses, int64_t
         po.buf[q] = static_cast<float *>(peer_bufs[q]);
     }
     po.world = world;
+    po.multicast = (flags & RL_GATHER_MULTICAST) ? 1 : 0;
     po.offset = (int64_t)rank * slot_rays;
     const int64_t total = num_poses * num_rays;
     const int64_t blocks = (total + CTA_THREADS - 1) / CTA_THREADS;

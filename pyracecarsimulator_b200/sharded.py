@@ -34,13 +34,21 @@ class _DevicePtr:
 
 
 class PeerGather:
-    """The fused march + all-gather: one gathered-ranges buffer per GPU (``world * slot_rays`` floats),
-    allocated by the C ABI, exchanged between the ranks as CUDA IPC handles and mapped into every
-    process, so that ``rl_calc_range_fan_allgather`` can store each range straight into slot ``rank`` of
-    all ``world`` buffers over NVLink while it marches (no separate collective, no staging copy).
-    ``sync()`` is the stream-ordered barrier after which every rank may read ``tensor()``."""
+    """The fused march + all-gather: one gathered-ranges buffer per GPU (``world * slot_rays`` floats)
+    mapped into every process, so that ``rl_calc_range_fan_allgather`` can store each range straight
+    into slot ``rank`` of all ``world`` buffers over NVLink while it marches (no separate collective,
+    no staging copy).  ``sync()`` is the stream-ordered barrier after which every rank may read
+    ``tensor()``.
 
-    def __init__(self, device_index: int, slot_rays: int, group: Optional[dist.ProcessGroup] = None):
+    backend "symm":  torch symmetric memory does the plumbing (allocation, rendezvous, signal-pad
+                     barrier); with ``multicast=True`` and NVLS support the kernel issues ONE
+                     ``multimem.st`` per range to the multicast address and the NVSwitch replicates it.
+    backend "ipc":   buffers allocated by the C ABI and exchanged as CUDA IPC handles; barrier = a
+                     4-byte NCCL all_reduce.  Used when symmetric memory is unavailable.
+    """
+
+    def __init__(self, device_index: int, slot_rays: int, group: Optional[dist.ProcessGroup] = None,
+                 backend: str = "auto", multicast: bool = True):
         import ctypes as C
         from . import _native
         self._native = _native
@@ -49,15 +57,53 @@ class PeerGather:
         self.rank = dist.get_rank(group)
         self.device_index = int(device_index)
         self.slot_rays = int(slot_rays)
-        L = _native.lib()
+        self.flags = 0
+        self._hdl = None
+        self._own = None
+        self._opened = []
+        n_floats = self.world * self.slot_rays
+        if backend in ("auto", "symm"):
+            try:
+                self._init_symm(n_floats, multicast)
+                self.backend = "symm"
+            except Exception as e:   # noqa: BLE001 - any failure of the optional plumbing -> IPC path
+                if backend == "symm":
+                    raise
+                self._symm_error = repr(e)
+                self._hdl = None
+        if self._hdl is None:
+            self._init_ipc(n_floats)
+            self.backend = "ipc"
+
+    def _init_symm(self, n_floats, multicast):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        dev = torch.device("cuda", self.device_index)
+        t = symm_mem.empty(n_floats, dtype=torch.float32, device=dev)
+        grp = self.group if self.group is not None else dist.group.WORLD
+        hdl = symm_mem.rendezvous(t, grp)
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        mc = int(hdl.multicast_ptr or 0) if multicast else 0   # 0 when the fabric has no NVLS multicast
+        # every rank must take the same decision
+        ok = torch.tensor([1 if mc else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 1:
+            self.flags = 1   # RL_GATHER_MULTICAST
+            self.ptrs = (C.c_void_p * self.world)(*([mc] + ptrs[1:]))
+        else:
+            self.ptrs = (C.c_void_p * self.world)(*ptrs)
+        self._view = t
+        self._hdl = hdl
+
+    def _init_ipc(self, n_floats):
+        import ctypes as C
+        L = self._native.lib()
         own = C.c_void_p()
         handle = (C.c_uint8 * 64)()
-        _native.check(L.rl_peer_alloc(self.device_index, self.world * self.slot_rays * 4, C.byref(own), handle),
-                      "rl_peer_alloc")
+        self._native.check(L.rl_peer_alloc(self.device_index, n_floats * 4, C.byref(own), handle), "rl_peer_alloc")
         self._own = own
         handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle), group=group)
-        self._opened = []
+        dist.all_gather_object(handles, bytes(handle), group=self.group)
         ptrs = []
         for q in range(self.world):
             if q == self.rank:
@@ -65,13 +111,16 @@ class PeerGather:
                 continue
             p = C.c_void_p()
             buf = (C.c_uint8 * 64).from_buffer_copy(handles[q])
-            _native.check(L.rl_peer_open(self.device_index, buf, C.byref(p)), "rl_peer_open")
+            self._native.check(L.rl_peer_open(self.device_index, buf, C.byref(p)), "rl_peer_open")
             self._opened.append(p)
             ptrs.append(p.value)
         self.ptrs = (C.c_void_p * self.world)(*ptrs)
         self._flag = torch.zeros(1, dtype=torch.int32, device=f"cuda:{self.device_index}")
-        self._view = torch.as_tensor(_DevicePtr(own.value, self.world * self.slot_rays),
-                                     device=f"cuda:{self.device_index}")
+        self._view = torch.as_tensor(_DevicePtr(own.value, n_floats), device=f"cuda:{self.device_index}")
+
+    @property
+    def multicast(self) -> bool:
+        return bool(self.flags & 1)
 
     def tensor(self) -> torch.Tensor:
         """This GPU's gathered buffer: (world * slot_rays,) float32, slot r = ranges of rank r."""
@@ -81,11 +130,14 @@ class PeerGather:
         n = poses.shape[0]
         self._native.check(self._native.lib().rl_calc_range_fan_allgather(
             marcher._h, poses.data_ptr(), 1, self.ptrs, self.world, self.rank, self.slot_rays, n, int(num_rays),
-            float(fov), stream_ptr), "rl_calc_range_fan_allgather")
+            float(fov), self.flags, stream_ptr), "rl_calc_range_fan_allgather")
 
     def sync(self):
         """Stream-ordered barrier: returns (on the stream) once every rank's march has completed."""
-        dist.all_reduce(self._flag, group=self.group)
+        if self._hdl is not None:
+            self._hdl.barrier()
+        else:
+            dist.all_reduce(self._flag, group=self.group)
 
     def close(self):
         """Collective: unmap every peer buffer on every rank before any rank frees its own."""
@@ -96,8 +148,9 @@ class PeerGather:
             L.rl_peer_close(self.device_index, p)
         self._opened = []
         dist.barrier(group=self.group)
+        self._view = None
+        self._hdl = None
         if self._own is not None:
-            self._view = None
             L.rl_peer_free(self.device_index, self._own)
             self._own = None
 

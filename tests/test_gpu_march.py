@@ -229,3 +229,43 @@ def test_rotated_origin_map(orc):
     out = np.zeros(400, np.float32)
     rm.calc_range_many(rays, out)
     assert_ranges_match(out, m.calc_range_many(rays), 0.1)
+
+
+def test_fused_allgather_kernel_two_virtual_ranks(big):
+    """rl_calc_range_fan_allgather on one GPU: two "ranks" (two gathered buffers on the same device)
+    each march their own shard and store into both buffers; both end up equal to the concatenation
+    of the two plain scans.  (The real multi-process path over NVLink is checked inside bench.py.)"""
+    import ctypes as C
+    import torch
+    from pyracecarsimulator_b200 import _native
+    L = _native.lib()
+    B, R = 64, 1080
+    poses = [maps.sample_free_poses(big["dist"], B, 900 + r, big["res"], big["origin"]) for r in range(2)]
+    slot = B * R + 128                      # padded slots, like uneven shards
+    bufs = []
+    for r in range(2):
+        p, h = C.c_void_p(), (C.c_uint8 * 64)()
+        _native.check(L.rl_peer_alloc(0, 2 * slot * 4, C.byref(p), h))
+        bufs.append(p)
+    ptrs = (C.c_void_p * 2)(bufs[0].value, bufs[1].value)
+    try:
+        for r in range(2):
+            dp = torch.from_numpy(poses[r]).cuda()
+            _native.check(L.rl_calc_range_fan_allgather(big["rm"]._h, dp.data_ptr(), 1, ptrs, 2, r, slot, B, R, FOV, 0, None))
+        torch.cuda.synchronize()
+        want = []
+        for r in range(2):
+            o = np.zeros(B * R, np.float32)
+            big["rm"].calc_range_fan(poses[r], o, FOV, R)
+            want.append(o)
+        for r in range(2):
+            from pyracecarsimulator_b200.sharded import _DevicePtr   # zero-copy view of the raw allocation
+            got = torch.as_tensor(_DevicePtr(bufs[r].value, 2 * slot), device="cuda").cpu().numpy()
+            assert np.array_equal(got[:B * R], want[0]) and np.array_equal(got[slot:slot + B * R], want[1])
+        # argument checks: slot too small, bad rank, too many peers
+        assert L.rl_calc_range_fan_allgather(big["rm"]._h, dp.data_ptr(), 1, ptrs, 2, 0, 10, B, R, FOV, 0, None) == _native.RL_ERR_BAD_ARG
+        assert L.rl_calc_range_fan_allgather(big["rm"]._h, dp.data_ptr(), 1, ptrs, 2, 2, slot, B, R, FOV, 0, None) == _native.RL_ERR_BAD_ARG
+        assert L.rl_calc_range_fan_allgather(big["rm"]._h, dp.data_ptr(), 1, ptrs, 17, 0, slot, B, R, FOV, 0, None) == _native.RL_ERR_BAD_ARG
+    finally:
+        for p in bufs:
+            L.rl_peer_free(0, p)
