@@ -558,6 +558,90 @@ __global__ void __launch_bounds__(128) k_phase2(Args a, Lean q, TailQ Q)
     }
 }
 
+// ---------------------------------------------------------------- V9: two copies of the distance field, row-major
+// and column-major; every ray reads the copy whose fast axis is its dominant direction, so that the
+// small steps it takes near walls stay inside one 32-byte sector (L1 hits) whichever way it travels.
+template <int MODE>   // 0: choose by |dx| vs |dy|; 1: always transposed (control)
+__global__ void __launch_bounds__(128) k_dual(Args a, Lean q, const float *__restrict__ distT)
+{
+    const unsigned i = blockIdx.x * 128u + threadIdx.x;
+    const unsigned total = (unsigned)a.num_poses * a.num_beams;
+    if (i >= total) return;
+    const MarchParams &P = a.P;
+    float x0, y0, dx, dy;
+    ray_setup_fan(a, q, i, x0, y0, dx, dy);
+    // x runs over rows (first index).  Row-major: idx = px*cols + py (fast axis = y).
+    const bool useT = MODE == 1 ? true : (fabsf(dx) > fabsf(dy));   // moving mostly along x: use the copy whose fast axis is x
+    const float *base = useT ? distT : P.dist;
+    const int sx = useT ? 1 : P.cols, sy = useT ? P.rows : 1;
+    float t = 0.f, r = P.max_range;
+    if ((x0 == x0) && (y0 == y0) && (dx == dx)) {
+        while (t < P.max_range) {
+            const int px = __float2int_rz(fmaf(dx, t, x0)), py = __float2int_rz(fmaf(dy, t, y0));
+            if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) break;
+            const float d = __ldg(base + (px * sx + py * sy));
+            if (d <= 0.0f) {
+                const float xd = __fsub_rn((float)px, x0), yd = __fsub_rn((float)py, y0);
+                r = sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+                break;
+            }
+            t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+        }
+    }
+    a.outs[i] = __fmul_rn(r, P.w.scale);
+}
+
+// ---------------------------------------------------------------- diagnostics: per-ray loop cycles and a timeline
+struct Diag { unsigned long long *t_first, *t_last; unsigned *hist_end_us; unsigned long long *long_cycles; unsigned *long_steps; unsigned *n_long;
+              unsigned long long *t0; };
+
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+template <int DUAL>
+__global__ void __launch_bounds__(128) k_diag(Args a, Lean q, Diag D, const float *__restrict__ distT)
+{
+    const unsigned i = blockIdx.x * 128u + threadIdx.x;
+    const unsigned total = (unsigned)a.num_poses * a.num_beams;
+    if (i >= total) return;
+    const MarchParams &P = a.P;
+    const unsigned long long tstart = gtime();
+    float x0, y0, dx, dy;
+    ray_setup_fan(a, q, i, x0, y0, dx, dy);
+    float t = 0.f, r = P.max_range;
+    unsigned steps = 0;
+    const bool useT = DUAL && (fabsf(dx) > fabsf(dy));
+    const float *base = useT ? distT : P.dist;
+    const int sx = useT ? 1 : P.cols, sy = useT ? P.rows : 1;
+    const long long c0 = clock64();
+    while (t < P.max_range) {
+        const int px = __float2int_rz(fmaf(dx, t, x0)), py = __float2int_rz(fmaf(dy, t, y0));
+        if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) break;
+        const float d = __ldg(base + (px * sx + py * sy));
+        ++steps;
+        if (d <= 0.0f) {
+            const float xd = __fsub_rn((float)px, x0), yd = __fsub_rn((float)py, y0);
+            r = sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+            break;
+        }
+        t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+    }
+    const long long c1 = clock64();
+    a.outs[i] = __fmul_rn(r, P.w.scale);
+    const unsigned long long tend = gtime();
+    // end-time histogram in microseconds since the first thread started (filled in a second pass on the host)
+    D.t_last[i >> 5] = tend;      // per warp (last writer wins, all lanes end together)
+    D.t_first[i >> 5] = tstart;
+    if (steps > 48) {
+        const unsigned slot = atomicAdd(D.n_long, 1u);
+        if (slot < 65536) { D.long_cycles[slot] = (unsigned long long)(c1 - c0); D.long_steps[slot] = steps; }
+    }
+}
+
 // ---------------------------------------------------------------- harness
 static std::vector<char> slurp(const std::string &path)
 {
@@ -692,7 +776,69 @@ int main(int argc, char **argv)
         R.run("ray3 opt3", [&] { k_ray3<3><<<b3, 128>>>(a, q); });
         R.run("ray3 opt7", [&] { k_ray3<7><<<b3, 128>>>(a, q); });
         R.run("ray3 opt5", [&] { k_ray3<5><<<b3, 128>>>(a, q); });
+        if (argc > 5) {
+            const int rows_ = a.P.rows, cols_ = a.P.cols;
+            const float *hd_ = (const float *)dist.data();
+            std::vector<float> tr_((size_t)rows_ * cols_);
+            for (int px = 0; px < rows_; ++px)
+                for (int py = 0; py < cols_; ++py) tr_[(size_t)py * rows_ + px] = hd_[(size_t)px * cols_ + py];
+            float *dT_;
+            CK(cudaMalloc(&dT_, tr_.size() * 4));
+            CK(cudaMemcpy(dT_, tr_.data(), tr_.size() * 4, cudaMemcpyHostToDevice));
+            for (int dual = 0; dual < 2; ++dual) {
+            printf("DIAG ===== dual layout %d\n", dual);
+            Diag D;
+            const size_t nwarps = (R.n_rays + 31) / 32;
+            CK(cudaMalloc(&D.t_first, nwarps * 8)); CK(cudaMalloc(&D.t_last, nwarps * 8));
+            CK(cudaMalloc(&D.long_cycles, 65536 * 8)); CK(cudaMalloc(&D.long_steps, 65536 * 4));
+            CK(cudaMalloc(&D.n_long, 4)); CK(cudaMalloc(&D.t0, 8));
+            for (int rep = 0; rep < 3; ++rep) {
+                CK(cudaMemset(D.n_long, 0, 4)); CK(cudaMemset(D.t0, 0xff, 8));
+                CK(cudaMemsetAsync(R.flush, rep, 256u << 20));
+                if (dual) k_diag<1><<<b3, 128>>>(a, q, D, dT_); else k_diag<0><<<b3, 128>>>(a, q, D, dT_);
+                CK(cudaDeviceSynchronize());
+            }
+            std::vector<unsigned long long> tf(nwarps), tl(nwarps), lc(65536);
+            std::vector<unsigned> ls(65536);
+            unsigned nl; unsigned long long t0;
+            CK(cudaMemcpy(tf.data(), D.t_first, nwarps * 8, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(tl.data(), D.t_last, nwarps * 8, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(lc.data(), D.long_cycles, 65536 * 8, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(ls.data(), D.long_steps, 65536 * 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(&nl, D.n_long, 4, cudaMemcpyDeviceToHost));
+            t0 = ~0ull; for (auto v : tf) t0 = v < t0 ? v : t0;
+            // timeline: warps running at each 4 us tick
+            unsigned long long tmax = 0; for (auto v : tl) tmax = v > tmax ? v : tmax;
+            printf("DIAG kernel span %.1f us, long rays (>48 steps): %u\n", (tmax - t0) / 1e3, nl);
+            for (unsigned long long tick = 0; tick <= (tmax - t0); tick += 4000) {
+                size_t running = 0, started = 0;
+                for (size_t w = 0; w < nwarps; ++w) { if (tf[w] - t0 <= tick) { ++started; if (tl[w] - t0 > tick) ++running; } }
+                printf("DIAG t=%5.1f us  warps started %7zu  running %6zu\n", tick / 1e3, started, running);
+            }
+            // per-step cycles of long rays, bucketed by steps
+            double cs[6] = {0}; unsigned cn[6] = {0}; const unsigned edges[7] = {48, 64, 96, 128, 192, 256, 100000};
+            unsigned long long worst = 0; unsigned worst_steps = 0;
+            for (unsigned k = 0; k < (nl < 65536 ? nl : 65536); ++k) {
+                for (int b = 0; b < 6; ++b) if (ls[k] > edges[b] && ls[k] <= edges[b + 1]) { cs[b] += (double)lc[k] / ls[k]; ++cn[b]; }
+                if (lc[k] > worst) { worst = lc[k]; worst_steps = ls[k]; }
+            }
+            for (int b = 0; b < 6; ++b) if (cn[b]) printf("DIAG rays with %u..%u steps: %u rays, %.0f cycles/step\n", edges[b], edges[b + 1], cn[b], cs[b] / cn[b]);
+            printf("DIAG slowest ray: %u steps, %llu cycles (%.1f us at 1.965 GHz)\n", worst_steps, worst, worst / 1965.0);
+            }
+        }
         {
+            const int rows = a.P.rows, cols = a.P.cols;
+            const float *hd = (const float *)dist.data();
+            std::vector<float> tr((size_t)rows * cols);
+            for (int px = 0; px < rows; ++px)
+                for (int py = 0; py < cols; ++py) tr[(size_t)py * rows + px] = hd[(size_t)px * cols + py];
+            float *dT;
+            CK(cudaMalloc(&dT, tr.size() * 4));
+            CK(cudaMemcpy(dT, tr.data(), tr.size() * 4, cudaMemcpyHostToDevice));
+            R.run("dual layout (row/col-major by ray direction)", [&] { k_dual<0><<<b3, 128>>>(a, q, dT); });
+            R.run("always transposed (control)", [&] { k_dual<1><<<b3, 128>>>(a, q, dT); });
+        }
+        if (argc > 4) {
             TailQ Q;
             Q.capacity = (unsigned)(R.n_rays / 4);
             CK(cudaMalloc(&Q.count, 4));
