@@ -24,21 +24,15 @@ class RacecarSimulator:
         self.verbose = verbose
         self.map_frame, self.base_frame, self.scan_frame = "map", "base_link", "laser"
         self.config = config
-        self.scan_dist_to_base = config["scan_dist_to_base"]
-        self.max_speed = config["max_speed"]
-        self.max_accel = config["max_accel"]
-        self.max_steer_ang = config["max_steer_ang"]
-        self.max_steer_vel = config["max_steer_vel"]
-        self.max_decel = config["max_decel"]
-        self.width = config["width"]
-        self.length = config["length"]
-        self.batch_size = config["batch_size"]
-        self.num_rays = config["scan_beams"]
-        self.scan_fov = config["scan_fov"]
-        self.scan_std = config["scan_std"]
-        self.scan_max_range = config["scan_max_range"]
-        self.free_thresh = config["free_thresh"]
-        self.ttc_thresh = config["ttc_thresh"]
+        # attribute <- config key, the names the reference facade exposes
+        # (scripts/racecar_simulator_v2.py:16-32)
+        for attr, key in (("scan_dist_to_base", "scan_dist_to_base"), ("max_speed", "max_speed"),
+                          ("max_accel", "max_accel"), ("max_steer_ang", "max_steer_ang"),
+                          ("max_steer_vel", "max_steer_vel"), ("max_decel", "max_decel"), ("width", "width"),
+                          ("length", "length"), ("batch_size", "batch_size"), ("num_rays", "scan_beams"),
+                          ("scan_fov", "scan_fov"), ("scan_std", "scan_std"), ("scan_max_range", "scan_max_range"),
+                          ("free_thresh", "free_thresh"), ("ttc_thresh", "ttc_thresh")):
+            setattr(self, attr, config[key])
 
         self.device = int(device)
         self._torch = torch

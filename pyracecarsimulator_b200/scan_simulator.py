@@ -39,23 +39,20 @@ _pinned_zeros._keep = []
 class ScanSimulator2D:
 
     def __init__(self, num_rays, fov, scan_std, batch_size=100):
-        self.batch_size = int(batch_size)
-        self.num_rays = int(num_rays)
-        self.fov = fov
-        self.scan_std = scan_std
-        self.twopi = math.pi * 2
-
-        self.output_vector = _pinned_zeros(self.num_rays)
-        self.noise = np.zeros(self.num_rays, dtype=np.float32)
-        self.input_vector = np.zeros((self.num_rays, 3), dtype=np.float32)
-
-        self.output_vector_many = _pinned_zeros(self.batch_size * self.num_rays)
-        # compact (batch_size, 3) pose block; the reference's (batch_size*num_rays, 3) layout, of
-        # which only every num_rays-th row is meaningful, is materialised on demand below
-        self.poses_many = _pinned_zeros((self.batch_size, 3))
-
-        self.hasMap = False
-        self.scan_method = None
+        self.num_rays, self.batch_size = int(num_rays), int(batch_size)
+        self.fov, self.scan_std = fov, scan_std
+        self.twopi = 2.0 * math.pi
+        n, b = self.num_rays, self.batch_size
+        # single-scan buffers: only row 0 of input_vector is ever meaningful (fork's 4-arg layout)
+        self.input_vector = np.zeros((n, 3), dtype=np.float32)
+        self.output_vector = _pinned_zeros(n)
+        self.noise = np.zeros(n, dtype=np.float32)
+        # batch buffers: a compact (batch_size, 3) pose block goes to the GPU; the reference's
+        # (batch_size*num_rays, 3) block, of which every num_rays-th row is meaningful, is
+        # materialised on demand by the property below
+        self.poses_many = _pinned_zeros((b, 3))
+        self.output_vector_many = _pinned_zeros(b * n)
+        self.hasMap, self.scan_method = False, None
 
     @property
     def input_vector_many(self) -> np.ndarray:
@@ -66,13 +63,9 @@ class ScanSimulator2D:
 
     def setMap(self, ros_map, max_range_px, resolution, origin):
         """ros_map: a ``range_libc.PyOMap``; max_range_px in pixels; origin (x, y, yaw)."""
-        self.omap = ros_map
-        self.origin_x = origin[0]
-        self.origin_y = origin[1]
-        self.origin_c = math.cos(origin[2])
-        self.origin_s = math.sin(origin[2])
-        self.mrx = max_range_px
-        self.res = resolution
+        self.omap, self.mrx, self.res = ros_map, max_range_px, resolution
+        self.origin_x, self.origin_y = origin[0], origin[1]
+        self.origin_c, self.origin_s = math.cos(origin[2]), math.sin(origin[2])
         self.hasMap = True
 
     def setRaytracingMethod(self, method="RM"):
@@ -96,11 +89,8 @@ class ScanSimulator2D:
     def scan(self, x, y, theta):
         if not self.hasMap or self.scan_method is None:
             raise RuntimeError("Doing a scan without a defined map / ray tracing method")
-        self.input_vector[0, 0] = x
-        self.input_vector[0, 1] = y
-        self.input_vector[0, 2] = theta
-        self.scan_method.calc_range_many(self.input_vector, self.output_vector, self.fov,
-                                         self.num_rays)
+        self.input_vector[0] = (x, y, theta)
+        self.scan_method.calc_range_many(self.input_vector, self.output_vector, self.fov, self.num_rays)
         return self.output_vector
 
     def scanMany(self, poses):
@@ -110,10 +100,7 @@ class ScanSimulator2D:
             self.poses_many[:] = poses[:self.batch_size, :3]
         else:
             for i in range(self.batch_size):
-                p = poses[i]
-                self.poses_many[i, 0] = p[0]
-                self.poses_many[i, 1] = p[1]
-                self.poses_many[i, 2] = p[2]
+                self.poses_many[i] = poses[i][0], poses[i][1], poses[i][2]
         self.scan_method.calc_range_fan(self.poses_many, self.output_vector_many, self.fov,
                                         self.num_rays)
         return self.output_vector_many
