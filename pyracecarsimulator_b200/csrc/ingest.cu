@@ -26,7 +26,6 @@
 namespace {
 
 constexpr uint32_t G_INF = 0xFFFFu;         // u16 column distance: no occupied cell in the column
-constexpr uint32_t G2_INF = 0xFFFFFFFFu;
 constexpr int MAX_SIDE = 16384;             // keeps every real d^2 below RL_DIST2_INF
 
 struct ByteLut { uint32_t w[8]; };          // bit p set <=> source byte p is an occupied cell
@@ -98,6 +97,13 @@ edt_cols_kernel(const uint8_t *__restrict__ occ, int rows, int cols, int nseg,
     }
 }
 
+// Row pass.  g2 in shared memory holds g^2, or G2_FAR for columns without any occupied cell;
+// G2_FAR + k^2 cannot wrap and stays above every real d^2 (<= 2 * 16384^2), so the scan needs no
+// special case for it.  Out-of-row neighbours are clamped to the row ends: the clamped candidate
+// k^2 + g2[end] is never below the true candidate (q - end)^2 + g2[end], so the minimum is
+// unchanged.  Four offsets are examined per trip (independent shared-memory loads, one exit test).
+constexpr uint32_t G2_FAR = 0x3fffffffu;
+
 __global__ void __launch_bounds__(256)
 edt_rows_kernel(const uint16_t *__restrict__ g, int rows, int cols,
                 int32_t *__restrict__ dist2, float *__restrict__ dist)
@@ -106,28 +112,29 @@ edt_rows_kernel(const uint16_t *__restrict__ g, int rows, int cols,
     const int r = blockIdx.x;
     const uint16_t *grow = g + (size_t)r * cols;
     for (int q = threadIdx.x; q < cols; q += blockDim.x) {
-        uint32_t v = grow[q];
-        g2[q] = (v >= G_INF) ? G2_INF : v * v;
+        const uint32_t v = grow[q];
+        g2[q] = (v >= G_INF) ? G2_FAR : v * v;
     }
     __syncthreads();
+    const int last = cols - 1;
     for (int q = threadIdx.x; q < cols; q += blockDim.x) {
         uint32_t best = g2[q];
-        const int reach = max(q, cols - 1 - q);
-        for (int k = 1; k <= reach; ++k) {
-            const uint32_t kk = (uint32_t)k * (uint32_t)k;
-            if (kk >= best) break;
-            const int l = q - k, rr = q + k;
-            if (l >= 0) {
-                uint32_t v = g2[l];
-                if (v != G2_INF) best = min(best, kk + v);
+        const int reach = max(q, last - q);
+        for (int k = 1; k <= reach; k += 4) {
+            if ((uint32_t)k * (uint32_t)k >= best) break;
+            uint32_t c[8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int kk = k + u;
+                const uint32_t k2 = (uint32_t)kk * (uint32_t)kk;
+                c[2 * u] = k2 + g2[max(q - kk, 0)];
+                c[2 * u + 1] = k2 + g2[min(q + kk, last)];
             }
-            if (rr < cols) {
-                uint32_t v = g2[rr];
-                if (v != G2_INF) best = min(best, kk + v);
-            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) best = min(best, c[u]);
         }
         const size_t o = (size_t)r * cols + q;
-        if (best == G2_INF) {
+        if (best >= G2_FAR) {
             dist2[o] = RL_DIST2_INF;
             dist[o] = sqrtf(1e20f);  // what the reference's INF = 1e20 transform leaves on an empty map
         } else {
