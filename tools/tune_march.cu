@@ -642,6 +642,63 @@ __global__ void __launch_bounds__(128) k_diag(Args a, Lean q, Diag D, const floa
     }
 }
 
+// ---------------------------------------------------------------- V10: tail mode.  After TAIL_AFTER plain steps a
+// ray switches to a loop that, besides each real sample, loads the cell AHEAD px further along the
+// ray into a ring of 4 registers that are only consumed 4 steps later, so the touch never stalls the
+// warp and the real sample finds its sector in L1.
+template <int AHEAD, int TAIL_AFTER, bool TOUCH = true>
+__global__ void __launch_bounds__(128) k_tail(Args a, Lean q)
+{
+    const unsigned i = blockIdx.x * 128u + threadIdx.x;
+    const unsigned total = (unsigned)a.num_poses * a.num_beams;
+    if (i >= total) return;
+    const MarchParams &P = a.P;
+    float x0, y0, dx, dy;
+    ray_setup_fan(a, q, i, x0, y0, dx, dy);
+    float t = 0.f, r = P.max_range;
+    bool done = !((x0 == x0) && (y0 == y0) && (dx == dx));
+    int it = 0;
+    while (!done) {
+        const int px = __float2int_rz(fmaf(dx, t, x0)), py = __float2int_rz(fmaf(dy, t, y0));
+        if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) { done = true; break; }
+        const float d = __ldg(P.dist + (px * P.cols + py));
+        if (d <= 0.0f) {
+            const float xd = __fsub_rn((float)px, x0), yd = __fsub_rn((float)py, y0);
+            r = sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+            done = true; break;
+        }
+        t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+        if (!(t < P.max_range)) { done = true; break; }
+        if (++it == TAIL_AFTER) break;
+    }
+    if (!done) {
+        float j0 = 0.f, j1 = 0.f, j2 = 0.f, j3 = 0.f, keep = 0.f;
+        const float adx = dx * (float)AHEAD, ady = dy * (float)AHEAD;
+#define TAIL_STEP(J)                                                                                  \
+        {                                                                                             \
+            const float fx = fmaf(dx, t, x0), fy = fmaf(dy, t, y0);                                   \
+            const int px = __float2int_rz(fx), py = __float2int_rz(fy);                               \
+            if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) break;          \
+            const float d = __ldg(P.dist + (px * P.cols + py));                                       \
+            const int ax = __float2int_rz(fx + adx), ay = __float2int_rz(fy + ady);                   \
+            keep += J;                                                                                \
+            if (TOUCH && (unsigned)ax < (unsigned)P.rows && (unsigned)ay < (unsigned)P.cols)          \
+                asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(J) : "l"(P.dist + (ax * P.cols + ay))); \
+            if (d <= 0.0f) {                                                                          \
+                const float xd = __fsub_rn((float)px, x0), yd = __fsub_rn((float)py, y0);             \
+                r = sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));                                           \
+                break;                                                                                \
+            }                                                                                         \
+            t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));                                      \
+            if (!(t < P.max_range)) break;                                                            \
+        }
+        for (;;) { TAIL_STEP(j0) TAIL_STEP(j1) TAIL_STEP(j2) TAIL_STEP(j3) }
+#undef TAIL_STEP
+        if (keep + j0 + j1 + j2 + j3 < 0.0f) r = -1.0f;   // never true (distances are >= 0): keeps the touches alive
+    }
+    a.outs[i] = __fmul_rn(r, P.w.scale);
+}
+
 // ---------------------------------------------------------------- harness
 static std::vector<char> slurp(const std::string &path)
 {
@@ -857,6 +914,21 @@ int main(int argc, char **argv)
             unsigned cnt; CK(cudaMemcpy(&cnt, Q.count, 4, cudaMemcpyDeviceToHost));
             printf("queue entries at last cap: %u\n", cnt);
         }
+        R.run("tail mode NO TOUCH after32 (control)", [&] { k_tail<12, 32, false><<<b3, 128>>>(a, q); });
+        R.run("tail mode NO TOUCH after1 (control)", [&] { k_tail<12, 1, false><<<b3, 128>>>(a, q); });
+        R.run("tail mode ahead12 after1", [&] { k_tail<12, 1><<<b3, 128>>>(a, q); });
+        R.run("tail mode ahead16 after32", [&] { k_tail<16, 32><<<b3, 128>>>(a, q); });
+        R.run("tail mode ahead24 after32", [&] { k_tail<24, 32><<<b3, 128>>>(a, q); });
+        R.run("tail mode ahead16 after20", [&] { k_tail<16, 20><<<b3, 128>>>(a, q); });
+        R.run("tail mode ahead12 after12", [&] { k_tail<12, 12><<<b3, 128>>>(a, q); });
+        R.run("tail mode ahead12 after8", [&] { k_tail<12, 8><<<b3, 128>>>(a, q); });
+        R.run("tail mode ahead32 after32", [&] { k_tail<32, 32><<<b3, 128>>>(a, q); });
+        R.run("tail mode ahead4 after32", [&] { k_tail<4, 32><<<b3, 128>>>(a, q); });
+        R.run("tail mode ahead8 after32", [&] { k_tail<8, 32><<<b3, 128>>>(a, q); });
+        R.run("tail mode ahead6 after16", [&] { k_tail<6, 16><<<b3, 128>>>(a, q); });
+        R.run("tail mode ahead8 after24", [&] { k_tail<8, 24><<<b3, 128>>>(a, q); });
+        R.run("tail mode ahead12 after32", [&] { k_tail<12, 32><<<b3, 128>>>(a, q); });
+        R.run("tail mode ahead8 after48", [&] { k_tail<8, 48><<<b3, 128>>>(a, q); });
         R.run("touch prefetch.L1 ahead4 near3", [&] { k_touch<4, 0><<<b3, 128>>>(a, q, 3.0f); });
         R.run("touch ld ahead4 near3", [&] { k_touch<4, 1><<<b3, 128>>>(a, q, 3.0f); });
         R.run("touch ld ahead3 near2", [&] { k_touch<3, 1><<<b3, 128>>>(a, q, 2.0f); });
