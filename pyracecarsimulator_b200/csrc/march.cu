@@ -2,6 +2,7 @@
 // Replaces range_libc's RayMarching / RayMarchingGPU calc_range_many (2-arg and the fork's
 // 4-arg fan) and calc_range_repeat_angles; reference call sites scripts/scan_simulator.py:103-106,
 // :130-133 and scripts/two_player/scan.py:69-70.
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -226,12 +227,16 @@ int32_t host_pipeline(rl_marcher *m, const float *ins, int64_t in_stride_floats,
             src = m->h_in;
         }
         float *dst = out_pinned ? outs + b * out_floats : m->h_out;
-        // a few sub-chunks of >= 512K ranges: every async call costs microseconds of host time, so
-        // the pipeline is kept shallow; small inputs (the fan's 12 B/pose) go up in one copy
-        int64_t nsub = (c * out_floats) >> 19;
-        nsub = nsub < 1 ? 1 : (nsub > 6 ? 6 : nsub);
-        if (nsub > c) nsub = c;
-        const int64_t per = (c + nsub - 1) / nsub;
+        // A few equal sub-chunks of >= 512K ranges (RL_HOST_SUBCHUNKS overrides the count, for
+        // experiments): every async call costs microseconds of host time, so the pipeline is kept
+        // shallow; small inputs (the fan's 12 B/pose) go up in one copy.
+        int64_t bounds[33];
+        int64_t want = (c * out_floats) >> 19;
+        want = want < 1 ? 1 : (want > 4 ? 4 : want);   // measured best on PCIe Gen5 (tools/e2e_probe.py)
+        if (const char *e = std::getenv("RL_HOST_SUBCHUNKS")) { const long v = std::atol(e); if (v >= 1 && v <= 32) want = v; }
+        if (want > c) want = c;
+        const int nsub = (int)want;
+        for (int i = 0; i <= nsub; ++i) bounds[i] = c * i / nsub;
         const bool one_h2d = (size_t)c * in_floats * sizeof(float) <= ((size_t)1 << 20);
         cudaEvent_t up = nullptr;
         if (one_h2d) {
@@ -242,9 +247,9 @@ int32_t host_pipeline(rl_marcher *m, const float *ins, int64_t in_stride_floats,
                 RL_CUDA(cudaStreamWaitEvent(st[1], up, 0));
             }
         }
-        int i = 0;
-        for (int64_t u = 0; u < c; u += per, ++i) {
-            const int64_t n = (c - u < per) ? c - u : per;
+        for (int i = 0; i < nsub; ++i) {
+            const int64_t u = bounds[i], n = bounds[i + 1] - bounds[i];
+            if (n <= 0) continue;
             cudaStream_t s = st[i & 1];
             if (!one_h2d)
                 RL_CUDA(cudaMemcpyAsync(m->d_in + u * in_floats, src + u * in_floats, (size_t)n * in_floats * sizeof(float),

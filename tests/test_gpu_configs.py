@@ -89,3 +89,28 @@ def test_config5_large_map_reduced_pose_count(orc):
     rm.calc_range_fan(poses, out, FOV, 270)
     want = orc.Marcher(dist, 300, y.resolution, y.origin).calc_range_fan(poses, 270, FOV, threads=0)
     assert_ranges_match(out, want, y.resolution)
+
+
+def test_more_than_2_31_rays_in_one_call(orc):
+    """One call with > 2^31 rays (config 5 is 4.3 G rays over 8 GPUs, > 2^31 per call on fewer GPUs):
+    exercises the 64-bit ray-index path.  Checked on the device against smaller calls over slices
+    (which take the 32-bit path, itself checked against the oracle above)."""
+    import torch
+    omap, y, occ, dist = build_synth(orc, 1025, 11)
+    rm = range_libc.PyRayMarchingGPU(omap, 300)
+    base = maps.sample_free_poses(dist, 65536, 606, y.resolution, y.origin)
+    beams = 270
+    n = 8_060_928                      # 123 * 65536 poses -> 2.176e9 rays
+    assert n * beams > 2 ** 31
+    poses = torch.from_numpy(np.tile(base, (n // 65536, 1))).cuda()
+    out = torch.empty(n * beams, dtype=torch.float32, device="cuda")
+    rm.calc_range_fan(poses, out, FOV, beams)
+    ref = torch.empty(65536 * beams, dtype=torch.float32, device="cuda")
+    rm.calc_range_fan(poses[:65536].contiguous(), ref, FOV, beams)
+    want = orc.Marcher(dist, 300, y.resolution, y.origin).calc_range_fan(base[:512], beams, FOV, threads=0)
+    assert np.array_equal(ref[:512 * beams].cpu().numpy(), want)
+    for blk in (0, 61, 122):           # first, middle (beyond 2^31 / 2), last tile
+        lo = blk * 65536 * beams
+        assert torch.equal(out[lo:lo + 65536 * beams], ref), blk
+    del out, poses
+    torch.cuda.empty_cache()
