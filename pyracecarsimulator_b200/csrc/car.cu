@@ -226,10 +226,11 @@ march_crash_kernel(rl::MarchParams P, const float *__restrict__ poses, const dou
     const float thw = __ldg(p + 2);
     const rl::GridPose gp = rl::world_to_grid(P.w, __ldg(p), __ldg(p + 1), thw);
     const float thg = __fadd_rn(-__fadd_rn(thw, fmaf((float)j, inc, -0.5f * fov)), P.w.rotation_const);
+    const rl::FirstSample f0 = rl::first_sample(P, gp.y, gp.x);
     float s, c;
     rl::glibc_sincosf(thg, &s, &c);
     uint32_t steps = 0;
-    const float r = __fmul_rn(rl::march_ray<false>(P, gp.y, gp.x, c, s, steps), P.w.scale);
+    const float r = __fmul_rn(rl::march_ray<false>(P, gp.y, gp.x, c, s, steps, f0), P.w.scale);
     if (WRITE) outs[i] = r;
     if (((double)r - __ldg(edge + j)) < thresh) atomicMin(first + g, pose_in_group);
 }

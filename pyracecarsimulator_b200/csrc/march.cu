@@ -36,9 +36,10 @@ march_many_kernel(MarchParams P, const float *__restrict__ ins, float *__restric
     uint32_t steps = 0;
     if (i < n) {
         const GridPose g = rl::world_to_grid(P.w, ins[3 * i], ins[3 * i + 1], ins[3 * i + 2]);
+        const rl::FirstSample f0 = rl::first_sample(P, g.y, g.x);
         float s, c;
         rl::glibc_sincosf(g.theta, &s, &c);
-        outs[i] = __fmul_rn(rl::march_ray<COUNT>(P, g.y, g.x, c, s, steps), P.w.scale);
+        outs[i] = __fmul_rn(rl::march_ray<COUNT>(P, g.y, g.x, c, s, steps, f0), P.w.scale);
     }
     flush_steps<COUNT>(steps, counter);
 }
@@ -86,9 +87,10 @@ march_pose_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_s
         float thg;
         if (FAN) thg = __fadd_rn(-__fadd_rn(thw, fmaf((float)j, inc, -0.5f * fov)), P.w.rotation_const);
         else thg = __fsub_rn(g.theta, __ldg(angles + j));
+        const rl::FirstSample f0 = rl::first_sample(P, g.y, g.x);
         float s, c;
         rl::glibc_sincosf(thg, &s, &c);
-        const float r = __fmul_rn(rl::march_ray<COUNT>(P, g.y, g.x, c, s, steps), P.w.scale);
+        const float r = __fmul_rn(rl::march_ray<COUNT>(P, g.y, g.x, c, s, steps, f0), P.w.scale);
         if (PEERS) {
             if (peers.multicast) {   // the NVSwitch replicates the store to all GPUs of the multicast group
                 asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(peers.buf[0] + peers.offset + i), "f"(r)

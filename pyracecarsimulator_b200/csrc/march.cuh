@@ -39,13 +39,38 @@ __device__ __forceinline__ GridPose world_to_grid(const WorldFrame &w, float xw,
 constexpr int TAIL_AFTER = 32;
 constexpr int TAIL_AHEAD = 12;
 
+// The first sample (t = 0) is the pose's own cell whatever the heading, so its load is issued
+// before the heading's sin/cos are evaluated and its latency hides behind that arithmetic.
+struct FirstSample {
+    int px, py;
+    float d;     // valid when inside
+    bool inside;
+};
+
+__device__ __forceinline__ FirstSample first_sample(const MarchParams &P, float x0, float y0)
+{
+    FirstSample f;
+    f.px = __float2int_rz(x0);   // fmaf(dx, 0, x0) == x0 for every finite dx
+    f.py = __float2int_rz(y0);
+    f.inside = (x0 == x0) && (y0 == y0) && (unsigned)f.px < (unsigned)P.rows && (unsigned)f.py < (unsigned)P.cols;
+    f.d = f.inside ? __ldg(P.dist + (f.px * P.cols + f.py)) : 0.0f;
+    return f;
+}
+
 template <bool COUNT>
 __device__ __forceinline__ float march_ray(const MarchParams &P, float x0, float y0, float dx,
-                                           float dy, uint32_t &steps)
+                                           float dy, uint32_t &steps, const FirstSample &f0)
 {
-    if (!(x0 == x0) || !(y0 == y0) || !(dx == dx) || !(dy == dy)) return P.max_range;
-    float t = 0.0f;
-    int it = 0;
+    if (!f0.inside || !(dx == dx) || !(dy == dy)) return P.max_range;   // NaN pose/heading or pose outside the map
+    if (COUNT) ++steps;
+    if (f0.d <= 0.0f) {   // pose inside an occupied cell: distance to that cell's corner
+        const float xd = __fsub_rn((float)f0.px, x0);
+        const float yd = __fsub_rn((float)f0.py, y0);
+        return sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+    }
+    float t = fmaxf(__fmul_rn(f0.d, 0.999f), 1.0f);   // 0 + step
+    if (!(t < P.max_range)) return P.max_range;
+    int it = 1;
     for (;;) {
         const int px = __float2int_rz(fmaf(dx, t, x0));
         const int py = __float2int_rz(fmaf(dy, t, y0));

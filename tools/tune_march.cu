@@ -47,9 +47,10 @@ __global__ void __launch_bounds__(WPC * 32) k_base(Args a, int segs, int seg_len
     float *o = a.outs + (size_t)k * a.num_beams;
     uint32_t st = 0;
     for (int j = seg * seg_len + lane; j < j_end; j += 32) {
+        const rl::FirstSample f0 = rl::first_sample(a.P, g.y, g.x);
         float s, c;
         rl::glibc_sincosf(beam_heading(a, thw, j), &s, &c);
-        o[j] = __fmul_rn(rl::march_ray<false>(a.P, g.y, g.x, c, s, st), a.P.w.scale);
+        o[j] = __fmul_rn(rl::march_ray<false>(a.P, g.y, g.x, c, s, st, f0), a.P.w.scale);
     }
 }
 
