@@ -342,10 +342,11 @@ def run_native(args, rank, world, local_rank):
         else:
             hbm_peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         gather_gbs = _native.gather_bandwidth(local_rank, dist_field.nbytes, 64, 10)
-        traffic = None
+        traffic, warp_insts = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic, warp_insts = tj.get("dram_bytes_per_launch"), tj.get("warp_insts_per_launch")
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                     "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                     "kernel": "march_pose_kernel<FAN>", "kernel_ms": kernel_ms,
@@ -353,6 +354,13 @@ def run_native(args, rank, world, local_rank):
                     "algorithmic_bytes_per_launch": alg_bytes, "march_steps_per_ray": mean_steps / n_rays,
                     "note": "the march is an L2-resident gather, not an HBM stream; l2_gather is the bound "
                             "BASELINE.json names",
+                    "issue": None if not (warp_insts and clocks.get("sm_mhz")) else {
+                        "achieved": warp_insts / (kernel_ms * 1e-3) / 1e9,
+                        "peak": 4 * torch.cuda.get_device_properties(local_rank).multi_processor_count * clocks["sm_mhz"] * 1e6 / 1e9,
+                        "unit": "G warp-instructions/s",
+                        "frac": warp_insts / (kernel_ms * 1e-3) / (4 * torch.cuda.get_device_properties(local_rank).multi_processor_count * clocks["sm_mhz"] * 1e6),
+                        "note": "what actually bounds the kernel: warp instructions per launch (ncu smsp__inst_executed.sum, "
+                                "profiles/traffic.json) over 4 issue slots per SM per clock"},
                     "l2_gather": {"achieved": achieved, "peak": gather_gbs, "unit": "GB/s",
                                   "frac": achieved / gather_gbs,
                                   "peak_source": "rl_gather_bandwidth: random 4-B gathers from a "
