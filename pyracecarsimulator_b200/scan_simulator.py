@@ -20,20 +20,15 @@ from . import range_libc
 
 
 def _pinned_zeros(shape, dtype=np.float32) -> np.ndarray:
-    """numpy view of page-locked host memory (plain numpy when torch/CUDA is unavailable)."""
+    """numpy view of page-locked host memory (plain numpy when torch/CUDA is unavailable).  The
+    returned array keeps its backing tensor alive through ``.base``."""
     try:
         import torch
         if torch.cuda.is_available():
-            t = torch.zeros(shape, dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
-            a = t.numpy()
-            _pinned_zeros._keep.append(t)
-            return a
+            return torch.zeros(shape, dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True).numpy()
     except ImportError:
         pass
     return np.zeros(shape, dtype=dtype)
-
-
-_pinned_zeros._keep = []
 
 
 class ScanSimulator2D:

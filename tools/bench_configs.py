@@ -47,6 +47,36 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     args = ap.parse_args()
 
+    # config 1: single-pose 1080-beam scan through ScanSimulator2D.scan (latency, host in / host out)
+    import time
+    from pyracecarsimulator_b200.scan_simulator import ScanSimulator2D
+    golden = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "colombia_map.npz")
+    z = np.load(golden)
+    path = "/tmp/_rl_cfg_colombia.pgm"
+    maps.write_pgm(path, z["img"])
+    yc = maps.MapYaml(path, float(z["resolution"]), tuple(float(v) for v in z["origin"]))
+    omap1 = range_libc.PyOMap(yc)
+    sim = ScanSimulator2D(1080, FOV, 0.01, batch_size=200)
+    sim.setMap(omap1, 300, yc.resolution, yc.origin)
+    sim.setRaytracingMethod("RMGPU")
+    for _ in range(20):
+        sim.scan(0.275, 0.0, 0.0)
+    t0 = time.perf_counter()
+    for _ in range(500):
+        sim.scan(0.275, 0.0, 0.0)
+    us = (time.perf_counter() - t0) / 500 * 1e6
+    poses200 = maps.sample_free_poses(omap1.dist(), 200, 7, yc.resolution, yc.origin)
+    for _ in range(20):
+        sim.scanMany(poses200)
+    t0 = time.perf_counter()
+    for _ in range(300):
+        sim.scanMany(poses200)
+    us200 = (time.perf_counter() - t0) / 300 * 1e6
+    print(json.dumps({"config": 1, "workload": "ScanSimulator2D.scan: 1 pose x 1080 beams on maps/colombia, host floats in, host ranges out",
+                      "us_per_scan": us, "rays_per_s": 1080 / (us * 1e-6),
+                      "scanMany_200_poses_us": us200, "scanMany_200_rays_per_s": 200 * 1080 / (us200 * 1e-6),
+                      "note": "reference budget: 20 Hz real-time = 50 000 us per scan; MCTS rollout batch = 200 poses"}))
+
     # config 3: particle filter, 1M poses x 60 angles on the 2049^2 stand-in
     omap, y, dist = synth(2049, 1234)
     rm = range_libc.PyRayMarchingGPU(omap, 300)
