@@ -205,3 +205,27 @@ class ShardedScanner:
         if self.rank != root:
             return None
         return torch.cat(parts)[:n * R]
+
+    def scan_fused(self, poses: torch.Tensor, marcher, fov: float, peer: "PeerGather" = None):
+        """All-gather fused into the march kernel (``rl_calc_range_fan_allgather``): every rank's ranges
+        are stored straight into every GPU's gathered buffer over NVLink while the march runs.
+        Returns the (N * num_rays,) gathered ranges (a view of the peer buffer, valid until the next
+        call) on every rank.  Pass a long-lived :class:`PeerGather` to avoid re-creating the mappings."""
+        n = poses.shape[0]
+        lo, hi = shard_bounds(n, self.world, self.rank)
+        per = -(-n // self.world) if n > 0 else 0
+        R = self.num_rays
+        if peer is None:
+            peer = self._peer if getattr(self, "_peer", None) is not None and self._peer.slot_rays >= per * R else None
+            if peer is None:
+                peer = self._peer = PeerGather(self.device.index, max(per * R, 1), self.group)
+        mine = poses[lo:hi].to(self.device).contiguous()
+        stream = int(torch.cuda.current_stream(self.device.index).cuda_stream)
+        peer.march(marcher, mine, fov, R, stream)
+        peer.sync()
+        full = peer.tensor()
+        if peer.slot_rays == per * R:
+            return full[:n * R]
+        # slots padded beyond this batch's shard size: compact the used parts
+        return torch.cat([full[r * peer.slot_rays: r * peer.slot_rays + max(0, min(n, (r + 1) * per) - r * per) * R]
+                          for r in range(self.world)])

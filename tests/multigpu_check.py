@@ -1,0 +1,60 @@
+"""Multi-GPU correctness check, run by hand on a box with >= 2 GPUs (not collected by pytest):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \\
+        --master-port 29555 tests/multigpu_check.py
+
+Every rank builds its replica of the map, then ShardedScanner's three NCCL gather modes and the fused
+peer-memory gather are compared bit for bit with the single-GPU scan of the whole batch."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pyracecarsimulator_b200 import maps, range_libc  # noqa: E402
+from pyracecarsimulator_b200.sharded import ShardedScanner, gpu_march_fn, shard_bounds  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    img = maps.synth_map(513, 21)
+    y = maps.synth_yaml(513)
+    path = f"/tmp/_mg_{rank}.pgm"
+    maps.write_pgm(path, img)
+    y.image = path
+    omap = range_libc.PyOMap(y, device=local)
+    rm = range_libc.PyRayMarchingGPU(omap, 300)
+    fov, R = 4.71, 270
+    ok = True
+    for n in (1001, 64, 7, 1):                       # uneven shards, fewer poses than ranks
+        poses = torch.from_numpy(maps.sample_free_poses(omap.dist(), n, 5 + n, y.resolution, y.origin))
+        want = torch.empty(n * R, dtype=torch.float32, device=dev)
+        rm.calc_range_fan(poses.to(dev), want, fov, R)           # whole batch on this GPU
+        sc = ShardedScanner(gpu_march_fn(rm, fov, R), R, dev)
+        got_all = sc.scan(poses, gather="all")
+        got_root = sc.scan(poses, gather="root")
+        got_none = sc.scan(poses, gather="none")
+        lo, hi = shard_bounds(n, world, rank)
+        got_fused = sc.scan_fused(poses, rm, fov).clone()
+        checks = [torch.equal(got_all, want), (got_root is None) if rank else torch.equal(got_root, want),
+                  torch.equal(got_none, want[lo * R:hi * R]), torch.equal(got_fused, want)]
+        ok = ok and all(checks)
+        if rank == 0:
+            print(f"n={n}: all={checks[0]} root={checks[1]} none={checks[2]} fused={checks[3]}")
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("MULTIGPU CHECK", "PASSED" if int(flag.item()) else "FAILED", f"(world {world})")
+    if getattr(sc, "_peer", None) is not None:
+        sc._peer.close()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()
