@@ -700,6 +700,53 @@ __global__ void __launch_bounds__(128) k_tail(Args a, Lean q)
     a.outs[i] = __fmul_rn(r, P.w.scale);
 }
 
+// ---------------------------------------------------------------- V11: persistent warps, static striding over
+// 32-ray groups for the first `static_groups`, then a shared atomic counter for the rest
+__global__ void __launch_bounds__(128) k_pstatic(Args a, Lean q, unsigned static_groups)
+{
+    const MarchParams &P = a.P;
+    const unsigned total = (unsigned)a.num_poses * a.num_beams;
+    const unsigned ngroups = (total + 31) / 32;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned nwarps = gridDim.x * 4;
+    unsigned g = blockIdx.x * 4 + (threadIdx.x >> 5);
+    bool dynamic = false;
+    for (;;) {
+        if (!dynamic) {
+            if (g >= static_groups) {
+                dynamic = true;
+                continue;
+            }
+        } else {
+            unsigned nx = 0;
+            if (lane == 0) nx = atomicAdd(a.counter, 1u);
+            g = static_groups + __shfl_sync(0xffffffffu, nx, 0);
+            if (g >= ngroups) break;
+        }
+        const unsigned i = g * 32 + lane;
+        if (i < total) {
+            float x0, y0, dx, dy;
+            ray_setup_fan(a, q, i, x0, y0, dx, dy);
+            const rl::FirstSample f0 = rl::first_sample(P, x0, y0);
+            uint32_t st = 0;
+            a.outs[i] = __fmul_rn(rl::march_ray<false>(P, x0, y0, dx, dy, st, f0), P.w.scale);
+        }
+        if (!dynamic) g += nwarps;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_product_like(Args a, Lean q)
+{
+    const unsigned i = blockIdx.x * 128u + threadIdx.x;
+    const unsigned total = (unsigned)a.num_poses * a.num_beams;
+    if (i >= total) return;
+    float x0, y0, dx, dy;
+    ray_setup_fan(a, q, i, x0, y0, dx, dy);
+    const rl::FirstSample f0 = rl::first_sample(a.P, x0, y0);
+    uint32_t st = 0;
+    a.outs[i] = __fmul_rn(rl::march_ray<false>(a.P, x0, y0, dx, dy, st, f0), a.P.w.scale);
+}
+
 // ---------------------------------------------------------------- harness
 static std::vector<char> slurp(const std::string &path)
 {
@@ -914,6 +961,16 @@ int main(int argc, char **argv)
             }
             unsigned cnt; CK(cudaMemcpy(&cnt, Q.count, 4, cudaMemcpyDeviceToHost));
             printf("queue entries at last cap: %u\n", cnt);
+        }
+        R.run("product-like (tail mode, first sample)", [&] { k_product_like<<<b3, 128>>>(a, q); });
+        {
+            const unsigned ngroups = (unsigned)((R.n_rays + 31) / 32);
+            for (int pct : {100, 90, 80, 60, 0}) {
+                for (int bps : {16, 12}) {
+                    char nm[96]; snprintf(nm, sizeof nm, "persistent static %d%% then atomic, %d CTAs/SM", pct, bps);
+                    R.run(nm, [&] { k_pstatic<<<sms * bps, 128>>>(a, q, (unsigned)((unsigned long long)ngroups * pct / 100)); });
+                }
+            }
         }
         R.run("tail mode NO TOUCH after32 (control)", [&] { k_tail<12, 32, false><<<b3, 128>>>(a, q); });
         R.run("tail mode NO TOUCH after1 (control)", [&] { k_tail<12, 1, false><<<b3, 128>>>(a, q); });
