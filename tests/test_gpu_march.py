@@ -269,3 +269,37 @@ def test_fused_allgather_kernel_two_virtual_ranks(big):
     finally:
         for p in bufs:
             L.rl_peer_free(0, p)
+
+
+def test_device_calls_on_concurrent_streams(big):
+    """Device-pointer calls are stateless: several host threads enqueue scans of different batches on
+    their own CUDA streams through ONE marcher; every result equals the serial one."""
+    import threading
+    import torch
+    batches = [torch.from_numpy(maps.sample_free_poses(big["dist"], 256, 700 + i, big["res"], big["origin"])).cuda()
+               for i in range(4)]
+    serial = []
+    for p in batches:
+        o = torch.empty(256 * 1080, dtype=torch.float32, device="cuda")
+        big["rm"].calc_range_fan(p, o, FOV, 1080)
+        serial.append(o)
+    torch.cuda.synchronize()
+    outs = [torch.zeros(256 * 1080, dtype=torch.float32, device="cuda") for _ in batches]
+    errs = []
+
+    def work(i):
+        try:
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                for _ in range(10):
+                    big["rm"].calc_range_fan(batches[i], outs[i], FOV, 1080)
+            s.synchronize()
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    for a, b in zip(outs, serial):
+        assert torch.equal(a, b)
