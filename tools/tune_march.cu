@@ -747,6 +747,51 @@ __global__ void __launch_bounds__(128) k_product_like(Args a, Lean q)
     a.outs[i] = __fmul_rn(rl::march_ray<false>(a.P, x0, y0, dx, dy, st, f0), a.P.w.scale);
 }
 
+// ---------------------------------------------------------------- V12: one 1024-thread CTA per pose with a TILE x TILE
+// window of the distance field around the pose staged in shared memory (SURVEY.md build plan step 8:
+// "keep only if it wins in measurement").  Samples inside the window read shared memory, others global.
+template <int TILE>
+__global__ void __launch_bounds__(1024) k_tile(Args a, Lean q)
+{
+    __shared__ float tile[TILE * TILE];
+    const MarchParams &P = a.P;
+    const int k = blockIdx.x;
+    const float *p = a.poses + 3 * k;
+    const float thw = __ldg(p + 2);
+    const GridPose g = rl::world_to_grid(P.w, __ldg(p), __ldg(p + 1), thw);
+    const float x0 = g.y, y0 = g.x;
+    const int cx = __float2int_rz(x0), cy = __float2int_rz(y0);
+    const int tx0 = cx - TILE / 2, ty0 = cy - TILE / 2;
+    for (int e = threadIdx.x; e < TILE * TILE; e += 1024) {
+        const int r = tx0 + e / TILE, c = ty0 + e % TILE;
+        tile[e] = ((unsigned)r < (unsigned)P.rows && (unsigned)c < (unsigned)P.cols) ? __ldg(P.dist + (r * P.cols + c)) : 1.0f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < a.num_beams; j += 1024) {
+        const float thg = __fadd_rn(-__fadd_rn(thw, fmaf((float)j, q.inc, -0.5f * a.fov)), P.w.rotation_const);
+        float dx, dy;
+        rl::glibc_sincosf(thg, &dy, &dx);
+        float t = 0.f, r = P.max_range;
+        if ((x0 == x0) && (y0 == y0) && (dx == dx)) {
+            while (t < P.max_range) {
+                const int px = __float2int_rz(fmaf(dx, t, x0)), py = __float2int_rz(fmaf(dy, t, y0));
+                if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) break;
+                const unsigned lx = (unsigned)(px - tx0), ly = (unsigned)(py - ty0);
+                float d;
+                if (lx < (unsigned)TILE && ly < (unsigned)TILE) d = tile[lx * TILE + ly];
+                else d = __ldg(P.dist + (px * P.cols + py));
+                if (d <= 0.0f) {
+                    const float xd = __fsub_rn((float)px, x0), yd = __fsub_rn((float)py, y0);
+                    r = sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+                    break;
+                }
+                t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+            }
+        }
+        a.outs[(size_t)k * a.num_beams + j] = __fmul_rn(r, P.w.scale);
+    }
+}
+
 // ---------------------------------------------------------------- harness
 static std::vector<char> slurp(const std::string &path)
 {
@@ -962,6 +1007,9 @@ int main(int argc, char **argv)
             unsigned cnt; CK(cudaMemcpy(&cnt, Q.count, 4, cudaMemcpyDeviceToHost));
             printf("queue entries at last cap: %u\n", cnt);
         }
+        R.run("smem tile 32x32 per pose (1024-thread CTA)", [&] { k_tile<32><<<a.num_poses, 1024>>>(a, q); });
+        R.run("smem tile 64x64 per pose (1024-thread CTA)", [&] { k_tile<64><<<a.num_poses, 1024>>>(a, q); });
+        R.run("smem tile 96x96 per pose (1024-thread CTA)", [&] { k_tile<96><<<a.num_poses, 1024>>>(a, q); });
         R.run("product-like (tail mode, first sample)", [&] { k_product_like<<<b3, 128>>>(a, q); });
         {
             const unsigned ngroups = (unsigned)((R.n_rays + 31) / 32);
