@@ -287,6 +287,27 @@ def run_native(args, rank, world, local_rank):
     e2e_s = time.perf_counter() - t0
     clocks = sampler.result()
 
+    # ---- the call MCTS actually makes on this batch: checkCollisionMany (scan + isCrashed), host poses in,
+    # one int back -- scan and crash test fused, the ranges never leave the GPU ----
+    from pyracecarsimulator_b200.racecar import BatchedCar
+    car = BatchedCar(device=local_rank)
+    car.setCarEdgeDistances(B, -FOV / 2.0, FOV / B, 0.275)
+    h_poses = torch.from_numpy(pose_sets[0]).pin_memory()
+    d_tmp = torch.empty((P, 3), dtype=torch.float32, device=dev)
+
+    def check_many(i):
+        d_tmp.copy_(h_poses, non_blocking=True)
+        first, _ = car.scan_crash(rm, d_tmp, 1, P, FOV)
+        return int(first.item())
+
+    for i in range(3):
+        check_many(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        crash_idx = check_many(i)
+    fused_s = time.perf_counter() - t0
+
     # ---- max over ranks ----
     # PCIe ceiling of the e2e path: pinned D2H of one step's ranges
     h_pin = torch.empty(n_rays, dtype=torch.float32, pin_memory=True)
@@ -406,6 +427,11 @@ def run_native(args, rank, world, local_rank):
                     "api": "ScanSimulator2D.scanMany(host poses) -> host ranges (pinned), per rank",
                     "pinned_d2h_gbs": d2h_gbs,
                     "pcie_bound_rays_per_s": world * d2h_gbs * 1e9 / 4.0},
+            "e2e_fused_crash": {"value": n_rays * e2e_steps / fused_s, "unit": "nominal rays/s per GPU",
+                                "ms_per_call": fused_s / e2e_steps * 1e3, "first_crash_index": crash_idx,
+                                "api": "checkCollisionMany semantics (scripts/racecar_simulator_v2.py:146-167): host poses in, "
+                                       "index of the first crashed pose out; rl_scan_crash skips every pose after it",
+                                "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "ingest_ms": omap.ingest_ms,
         }
