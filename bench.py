@@ -180,6 +180,8 @@ def run_native(args, rank, world, local_rank):
     dist_on = world > 1
     if dist_on:
         import torch.distributed as tdist
+        # NCCL writes its version / debug lines to stdout by default: keep stdout for the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         tdist.init_process_group("nccl", device_id=dev)
 
     def barrier():
