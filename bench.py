@@ -178,10 +178,13 @@ def run_native(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist_on = world > 1
+    # Libraries (NCCL's version / debug lines) write to stdout: point fd 1 at stderr while the benchmark
+    # runs and give it back only for the one JSON line.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if dist_on:
         import torch.distributed as tdist
-        # NCCL writes its version / debug lines to stdout by default: keep stdout for the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         tdist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -451,7 +454,10 @@ def run_native(args, rank, world, local_rank):
             line["gather_nccl"] = entry(ms_nccl, "march, then NCCL all_gather_into_tensor of the ranges")
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if peer is not None:
         peer.close()
     if dist_on:
