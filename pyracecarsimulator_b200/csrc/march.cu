@@ -229,6 +229,21 @@ int32_t host_pipeline(rl_marcher *m, const float *ins, int64_t in_stride_floats,
             src = m->h_in;
         }
         float *dst = out_pinned ? outs + b * out_floats : m->h_out;
+        // Zero-copy output: when the caller's buffer is page-locked (mapped under unified addressing) the
+        // march kernel stores its ranges straight into it over PCIe -- no device->host copy to wait for,
+        // the transfer overlaps the march warp by warp.  RL_HOST_ZEROCOPY=0 falls back to the staged path.
+        static const bool zero_copy_ok = [] { const char *e = std::getenv("RL_HOST_ZEROCOPY"); return !(e && e[0] == '0'); }();
+        if (out_pinned && zero_copy_ok) {
+            float *d_alias = nullptr;
+            if (cudaHostGetDevicePointer((void **)&d_alias, dst, 0) == cudaSuccess && d_alias) {
+                RL_CUDA(cudaMemcpyAsync(m->d_in, src, (size_t)c * in_floats * sizeof(float), cudaMemcpyHostToDevice, st[0]));
+                rc = launch(0, c, m->d_in, d_alias, st[0]);
+                if (rc != RL_OK) return rc;
+                RL_CUDA(cudaStreamSynchronize(st[0]));
+                continue;
+            }
+            cudaGetLastError();
+        }
         // A few equal sub-chunks of >= 512K ranges (RL_HOST_SUBCHUNKS overrides the count, for
         // experiments): every async call costs microseconds of host time, so the pipeline is kept
         // shallow; small inputs (the fan's 12 B/pose) go up in one copy.
