@@ -70,49 +70,51 @@ __device__ __forceinline__ float march_ray(const MarchParams &P, float x0, float
     }
     float t = fmaxf(__fmul_rn(f0.d, 0.999f), 1.0f);   // 0 + step
     if (!(t < P.max_range)) return P.max_range;
-    int it = 1;
+    // One exit branch per step: t is advanced before the hit test (harmless: a hit ends the ray) and
+    // which of the two exits it was is decided once, after the loop.
+    int px, py, it = 1;
+    float d;
+    bool tail = false;
     for (;;) {
-        const int px = __float2int_rz(fmaf(dx, t, x0));
-        const int py = __float2int_rz(fmaf(dy, t, y0));
+        px = __float2int_rz(fmaf(dx, t, x0));
+        py = __float2int_rz(fmaf(dy, t, y0));
         if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) return P.max_range;
-        const float d = __ldg(P.dist + (px * P.cols + py));
+        d = __ldg(P.dist + (px * P.cols + py));
         if (COUNT) ++steps;
-        if (d <= 0.0f) {
-            const float xd = __fsub_rn((float)px, x0);
-            const float yd = __fsub_rn((float)py, y0);
-            return sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
-        }
         t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
-        if (!(t < P.max_range)) return P.max_range;
-        if (++it == TAIL_AFTER) break;
+        if (d <= 0.0f || !(t < P.max_range)) break;
+        if (++it == TAIL_AFTER) { tail = true; break; }
     }
-    // ---- tail mode ----
-    float r = P.max_range;
-    float j0 = 0.f, j1 = 0.f, j2 = 0.f, j3 = 0.f, keep = 0.f;
-    const float adx = __fmul_rn(dx, (float)TAIL_AHEAD), ady = __fmul_rn(dy, (float)TAIL_AHEAD);
+    if (tail) {
+        float j0 = 0.f, j1 = 0.f, j2 = 0.f, j3 = 0.f, keep = 0.f;
+        const float adx = __fmul_rn(dx, (float)TAIL_AHEAD), ady = __fmul_rn(dy, (float)TAIL_AHEAD);
+        bool inside = true;
 #define RL_TAIL_STEP(J)                                                                            \
-    {                                                                                              \
-        const float fx = fmaf(dx, t, x0), fy = fmaf(dy, t, y0);                                    \
-        const int px = __float2int_rz(fx), py = __float2int_rz(fy);                                \
-        if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) break;           \
-        const float d = __ldg(P.dist + (px * P.cols + py));                                        \
-        if (COUNT) ++steps;                                                                        \
-        const int ax = __float2int_rz(__fadd_rn(fx, adx)), ay = __float2int_rz(__fadd_rn(fy, ady)); \
-        keep = __fadd_rn(keep, J);                                                                 \
-        if ((unsigned)ax < (unsigned)P.rows && (unsigned)ay < (unsigned)P.cols)                    \
-            asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(J) : "l"(P.dist + (ax * P.cols + ay))); \
-        if (d <= 0.0f) {                                                                           \
-            const float xd = __fsub_rn((float)px, x0), yd = __fsub_rn((float)py, y0);              \
-            r = sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));                                            \
-            break;                                                                                 \
-        }                                                                                          \
-        t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));                                       \
-        if (!(t < P.max_range)) break;                                                             \
-    }
-    for (;;) { RL_TAIL_STEP(j0) RL_TAIL_STEP(j1) RL_TAIL_STEP(j2) RL_TAIL_STEP(j3) }
+        {                                                                                          \
+            const float fx = fmaf(dx, t, x0), fy = fmaf(dy, t, y0);                                \
+            px = __float2int_rz(fx);                                                               \
+            py = __float2int_rz(fy);                                                               \
+            if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) { inside = false; break; } \
+            d = __ldg(P.dist + (px * P.cols + py));                                                \
+            if (COUNT) ++steps;                                                                    \
+            const int ax = __float2int_rz(__fadd_rn(fx, adx)), ay = __float2int_rz(__fadd_rn(fy, ady)); \
+            keep = __fadd_rn(keep, J);                                                             \
+            if ((unsigned)ax < (unsigned)P.rows && (unsigned)ay < (unsigned)P.cols)                \
+                asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(J) : "l"(P.dist + (ax * P.cols + ay))); \
+            t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));                                   \
+            if (d <= 0.0f || !(t < P.max_range)) break;                                            \
+        }
+        for (;;) { RL_TAIL_STEP(j0) RL_TAIL_STEP(j1) RL_TAIL_STEP(j2) RL_TAIL_STEP(j3) }
 #undef RL_TAIL_STEP
-    if (__fadd_rn(__fadd_rn(keep, j0), __fadd_rn(j1, __fadd_rn(j2, j3))) < 0.0f) r = -1.0f;  // never true
-    return r;
+        if (__fadd_rn(__fadd_rn(keep, j0), __fadd_rn(j1, __fadd_rn(j2, j3))) < 0.0f) return -1.0f;  // never true
+        if (!inside) return P.max_range;
+    }
+    if (d <= 0.0f) {
+        const float xd = __fsub_rn((float)px, x0);
+        const float yd = __fsub_rn((float)py, y0);
+        return sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+    }
+    return P.max_range;
 }
 
 // Unsigned division by a launch-constant divisor d >= 2, exact for numerators below 2^31:

@@ -792,6 +792,38 @@ __global__ void __launch_bounds__(1024) k_tile(Args a, Lean q)
     }
 }
 
+// ---------------------------------------------------------------- V13: product loop with the hit / max-range exits
+// merged into one branch per step (t is advanced speculatively; which exit it was is sorted out after the loop)
+__global__ void __launch_bounds__(128, 16) k_merged(Args a, Lean q)
+{
+    const unsigned i = blockIdx.x * 128u + threadIdx.x;
+    const unsigned total = (unsigned)a.num_poses * a.num_beams;
+    if (i >= total) return;
+    const MarchParams &P = a.P;
+    float x0, y0, dx, dy;
+    ray_setup_fan(a, q, i, x0, y0, dx, dy);
+    float r = P.max_range;
+    if ((x0 == x0) && (y0 == y0) && (dx == dx)) {
+        float t = 0.f, d = 1.f;
+        int px = 0, py = 0;
+        bool inb = true;
+        for (;;) {
+            px = __float2int_rz(fmaf(dx, t, x0));
+            py = __float2int_rz(fmaf(dy, t, y0));
+            inb = (unsigned)px < (unsigned)P.rows && (unsigned)py < (unsigned)P.cols;
+            if (!inb) break;
+            d = __ldg(P.dist + (px * P.cols + py));
+            t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+            if (d <= 0.0f || !(t < P.max_range)) break;
+        }
+        if (inb && d <= 0.0f) {
+            const float xd = __fsub_rn((float)px, x0), yd = __fsub_rn((float)py, y0);
+            r = sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+        }
+    }
+    a.outs[i] = __fmul_rn(r, P.w.scale);
+}
+
 // ---------------------------------------------------------------- harness
 static std::vector<char> slurp(const std::string &path)
 {
@@ -1010,6 +1042,7 @@ int main(int argc, char **argv)
         R.run("smem tile 32x32 per pose (1024-thread CTA)", [&] { k_tile<32><<<a.num_poses, 1024>>>(a, q); });
         R.run("smem tile 64x64 per pose (1024-thread CTA)", [&] { k_tile<64><<<a.num_poses, 1024>>>(a, q); });
         R.run("smem tile 96x96 per pose (1024-thread CTA)", [&] { k_tile<96><<<a.num_poses, 1024>>>(a, q); });
+        R.run("merged exits (no tail mode)", [&] { k_merged<<<b3, 128>>>(a, q); });
         R.run("product-like (tail mode, first sample)", [&] { k_product_like<<<b3, 128>>>(a, q); });
         {
             const unsigned ngroups = (unsigned)((R.n_rays + 31) / 32);
