@@ -34,8 +34,6 @@ struct rl_car {
     int num_rays = 0;
     std::vector<double> edge;   // host copy (computed with the host libm, like the reference)
     double *d_edge = nullptr;
-    int32_t *d_first = nullptr; // scratch for *_host variants
-    size_t cap_first = 0;
 };
 
 namespace {
@@ -293,7 +291,6 @@ RL_API int32_t rl_car_destroy(rl_car *car)
     {
         rl::DeviceGuard guard(car->device);
         cudaFree(car->d_edge);
-        cudaFree(car->d_first);
     }
     delete car;
     return RL_OK;

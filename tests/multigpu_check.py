@@ -31,11 +31,11 @@ def main():
     rm = range_libc.PyRayMarchingGPU(omap, 300)
     fov, R = 4.71, 270
     ok = True
+    sc = ShardedScanner(gpu_march_fn(rm, fov, R), R, dev)
     for n in (1001, 64, 7, 1):                       # uneven shards, fewer poses than ranks
         poses = torch.from_numpy(maps.sample_free_poses(omap.dist(), n, 5 + n, y.resolution, y.origin))
         want = torch.empty(n * R, dtype=torch.float32, device=dev)
         rm.calc_range_fan(poses.to(dev), want, fov, R)           # whole batch on this GPU
-        sc = ShardedScanner(gpu_march_fn(rm, fov, R), R, dev)
         got_all = sc.scan(poses, gather="all")
         got_root = sc.scan(poses, gather="root")
         got_none = sc.scan(poses, gather="none")
