@@ -824,6 +824,74 @@ __global__ void __launch_bounds__(128, 16) k_merged(Args a, Lean q)
     a.outs[i] = __fmul_rn(r, P.w.scale);
 }
 
+// ---------------------------------------------------------------- V14: value-predicted tail.  Creeping rays see the
+// same clearance d step after step (90 % of tail steps on axis-aligned walls), so after TAIL steps a ray
+// loads, together with its real sample at t, the samples at t+s, t+2s, t+3s that it WOULD take if d
+// repeated (s = step(d_prev)), then walks through them while the prediction holds: same t values bit
+// for bit, but one memory round trip and one address chain per four steps instead of per step.
+template <int TAIL, int DEPTH>
+__global__ void __launch_bounds__(128) k_spec(Args a, Lean q)
+{
+    const unsigned i = blockIdx.x * 128u + threadIdx.x;
+    const unsigned total = (unsigned)a.num_poses * a.num_beams;
+    if (i >= total) return;
+    const MarchParams &P = a.P;
+    float x0, y0, dx, dy;
+    ray_setup_fan(a, q, i, x0, y0, dx, dy);
+    float r = P.max_range;
+    if ((x0 == x0) && (y0 == y0) && (dx == dx)) {
+        float t = 0.f, d = 1.f;
+        int px = 0, py = 0, it = 0;
+        bool inb = true, tail = false;
+        for (;;) {
+            px = __float2int_rz(fmaf(dx, t, x0));
+            py = __float2int_rz(fmaf(dy, t, y0));
+            inb = (unsigned)px < (unsigned)P.rows && (unsigned)py < (unsigned)P.cols;
+            if (!inb) break;
+            d = __ldg(P.dist + (px * P.cols + py));
+            t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+            if (d <= 0.0f || !(t < P.max_range)) break;
+            if (++it == TAIL) { tail = true; break; }
+        }
+        if (tail) {
+            // here: d = last clearance (> 0), t = parameter of the next sample (< max_range)
+            bool finished = false;
+            while (!finished) {
+                const float s = fmaxf(__fmul_rn(d, 0.999f), 1.0f);
+                float tt[DEPTH], vv[DEPTH];
+                int cx[DEPTH], cy[DEPTH];
+                bool ok[DEPTH];
+                tt[0] = t;
+#pragma unroll
+                for (int k = 1; k < DEPTH; ++k) tt[k] = __fadd_rn(tt[k - 1], s);
+#pragma unroll
+                for (int k = 0; k < DEPTH; ++k) {
+                    cx[k] = __float2int_rz(fmaf(dx, tt[k], x0));
+                    cy[k] = __float2int_rz(fmaf(dy, tt[k], y0));
+                    ok[k] = (unsigned)cx[k] < (unsigned)P.rows && (unsigned)cy[k] < (unsigned)P.cols;
+                    vv[k] = ok[k] ? __ldg(P.dist + (cx[k] * P.cols + cy[k])) : 0.0f;
+                }
+                const float dprev = d;
+#pragma unroll
+                for (int k = 0; k < DEPTH; ++k) {
+                    // sample k is real iff every earlier sample of this round repeated dprev
+                    px = cx[k]; py = cy[k];
+                    if (!ok[k]) { inb = false; finished = true; break; }
+                    d = vv[k];
+                    t = __fadd_rn(tt[k], fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+                    if (d <= 0.0f || !(t < P.max_range)) { finished = true; break; }
+                    if (d != dprev) break;   // prediction ends here: next round starts from the true t
+                }
+            }
+        }
+        if (inb && d <= 0.0f) {
+            const float xd = __fsub_rn((float)px, x0), yd = __fsub_rn((float)py, y0);
+            r = sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+        }
+    }
+    a.outs[i] = __fmul_rn(r, P.w.scale);
+}
+
 // ---------------------------------------------------------------- harness
 static std::vector<char> slurp(const std::string &path)
 {
@@ -1042,6 +1110,12 @@ int main(int argc, char **argv)
         R.run("smem tile 32x32 per pose (1024-thread CTA)", [&] { k_tile<32><<<a.num_poses, 1024>>>(a, q); });
         R.run("smem tile 64x64 per pose (1024-thread CTA)", [&] { k_tile<64><<<a.num_poses, 1024>>>(a, q); });
         R.run("smem tile 96x96 per pose (1024-thread CTA)", [&] { k_tile<96><<<a.num_poses, 1024>>>(a, q); });
+        R.run("value-predicted tail after32 depth4", [&] { k_spec<32, 4><<<b3, 128>>>(a, q); });
+        R.run("value-predicted tail after32 depth3", [&] { k_spec<32, 3><<<b3, 128>>>(a, q); });
+        R.run("value-predicted tail after32 depth6", [&] { k_spec<32, 6><<<b3, 128>>>(a, q); });
+        R.run("value-predicted tail after16 depth4", [&] { k_spec<16, 4><<<b3, 128>>>(a, q); });
+        R.run("value-predicted tail after24 depth4", [&] { k_spec<24, 4><<<b3, 128>>>(a, q); });
+        R.run("value-predicted tail after48 depth4", [&] { k_spec<48, 4><<<b3, 128>>>(a, q); });
         R.run("merged exits (no tail mode)", [&] { k_merged<<<b3, 128>>>(a, q); });
         R.run("product-like (tail mode, first sample)", [&] { k_product_like<<<b3, 128>>>(a, q); });
         {
