@@ -892,6 +892,66 @@ __global__ void __launch_bounds__(128) k_spec(Args a, Lean q)
     a.outs[i] = __fmul_rn(r, P.w.scale);
 }
 
+// ---------------------------------------------------------------- V15: value-predicted tail, registers only
+template <int TAIL>
+__global__ void __launch_bounds__(128) k_spec2(Args a, Lean q)
+{
+    const unsigned i = blockIdx.x * 128u + threadIdx.x;
+    const unsigned total = (unsigned)a.num_poses * a.num_beams;
+    if (i >= total) return;
+    const MarchParams &P = a.P;
+    float x0, y0, dx, dy;
+    ray_setup_fan(a, q, i, x0, y0, dx, dy);
+    float r = P.max_range;
+    if ((x0 == x0) && (y0 == y0) && (dx == dx)) {
+        float t = 0.f, d = 1.f, th = 0.f;   // th: parameter of the sample that hit
+        int it = 0;
+        int state = 0;                      // 0 running, 1 hit at th, 2 max range / left the map
+        for (;;) {
+            const int px = __float2int_rz(fmaf(dx, t, x0)), py = __float2int_rz(fmaf(dy, t, y0));
+            if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) { state = 2; break; }
+            d = __ldg(P.dist + (px * P.cols + py));
+            th = t;
+            t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+            if (d <= 0.0f) { state = 1; break; }
+            if (!(t < P.max_range)) { state = 2; break; }
+            if (++it == TAIL) break;
+        }
+        while (state == 0) {
+            const float s = fmaxf(__fmul_rn(d, 0.999f), 1.0f);
+            const float ta = t, tb = __fadd_rn(ta, s), tc = __fadd_rn(tb, s), td = __fadd_rn(tc, s);
+            float va = 0.f, vb = 0.f, vc = 0.f, vd = 0.f;
+            unsigned ok = 0;
+#define SPEC_LOAD(T, V, BIT)                                                                         \
+            {                                                                                        \
+                const int cx = __float2int_rz(fmaf(dx, T, x0)), cy = __float2int_rz(fmaf(dy, T, y0)); \
+                if ((unsigned)cx < (unsigned)P.rows && (unsigned)cy < (unsigned)P.cols) {            \
+                    V = __ldg(P.dist + (cx * P.cols + cy));                                          \
+                    ok |= BIT;                                                                       \
+                }                                                                                    \
+            }
+            SPEC_LOAD(ta, va, 1u) SPEC_LOAD(tb, vb, 2u) SPEC_LOAD(tc, vc, 4u) SPEC_LOAD(td, vd, 8u)
+#undef SPEC_LOAD
+            const float dprev = d;
+#define SPEC_USE(T, V, BIT)                                                                          \
+            if (!(ok & BIT)) { state = 2; break; }                                                   \
+            d = V; th = T;                                                                           \
+            t = __fadd_rn(T, fmaxf(__fmul_rn(d, 0.999f), 1.0f));                                     \
+            if (d <= 0.0f) { state = 1; break; }                                                     \
+            if (!(t < P.max_range)) { state = 2; break; }                                            \
+            if (d != dprev) continue;
+            SPEC_USE(ta, va, 1u) SPEC_USE(tb, vb, 2u) SPEC_USE(tc, vc, 4u) SPEC_USE(td, vd, 8u)
+#undef SPEC_USE
+        }
+        if (state == 1) {
+            const int px = __float2int_rz(fmaf(dx, th, x0)), py = __float2int_rz(fmaf(dy, th, y0));
+            const float xd = __fsub_rn((float)px, x0), yd = __fsub_rn((float)py, y0);
+            r = sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+        }
+    }
+    a.outs[i] = __fmul_rn(r, P.w.scale);
+}
+
 // ---------------------------------------------------------------- harness
 static std::vector<char> slurp(const std::string &path)
 {
@@ -1110,6 +1170,10 @@ int main(int argc, char **argv)
         R.run("smem tile 32x32 per pose (1024-thread CTA)", [&] { k_tile<32><<<a.num_poses, 1024>>>(a, q); });
         R.run("smem tile 64x64 per pose (1024-thread CTA)", [&] { k_tile<64><<<a.num_poses, 1024>>>(a, q); });
         R.run("smem tile 96x96 per pose (1024-thread CTA)", [&] { k_tile<96><<<a.num_poses, 1024>>>(a, q); });
+        R.run("value-predicted tail (registers) after32", [&] { k_spec2<32><<<b3, 128>>>(a, q); });
+        R.run("value-predicted tail (registers) after16", [&] { k_spec2<16><<<b3, 128>>>(a, q); });
+        R.run("value-predicted tail (registers) after8", [&] { k_spec2<8><<<b3, 128>>>(a, q); });
+        R.run("value-predicted tail (registers) after24", [&] { k_spec2<24><<<b3, 128>>>(a, q); });
         R.run("value-predicted tail after32 depth4", [&] { k_spec<32, 4><<<b3, 128>>>(a, q); });
         R.run("value-predicted tail after32 depth3", [&] { k_spec<32, 3><<<b3, 128>>>(a, q); });
         R.run("value-predicted tail after32 depth6", [&] { k_spec<32, 6><<<b3, 128>>>(a, q); });
