@@ -221,7 +221,8 @@ def run_native(args, rank, world, local_rank):
     def step(i, ev0=None, ev1=None, how=None):
         how = mode if how is None else how
         if flush is not None:
-            flush.fill_(i & 0xFF)          # 256 MiB write > 126 MB L2: evicts the distance field
+            flush.fill_(i & 0xFF)          # 256 MiB write > 126 MB L2 ...
+            _native.lib().rl_l2_reset_persisting(local_rank)   # ... and un-pin the distance field, so it is evicted too
         if ev0 is not None:
             ev0.record()
         if how == "p2p":
@@ -345,6 +346,7 @@ def run_native(args, rank, world, local_rank):
         for i in range(min(K, 50)):
             if flush is not None:
                 flush.fill_(i & 0xFF)
+                _native.lib().rl_l2_reset_persisting(local_rank)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             rm.calc_range_fan(d_poses[i % n_sets], d_out, FOV, B)
@@ -361,6 +363,17 @@ def run_native(args, rank, world, local_rank):
             warm_ms.append((a, b))
         torch.cuda.synchronize()
         warm_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in warm_ms]))
+        pinned_ms = []
+        for i in range(min(K, 50)):   # L2 flushed, distance field left pinned by the product's access-policy window
+            if flush is not None:
+                flush.fill_(i & 0xFF)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            rm.calc_range_fan(d_poses[i % n_sets], d_out, FOV, B)
+            b.record()
+            pinned_ms.append((a, b))
+        torch.cuda.synchronize()
+        pinned_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in pinned_ms]))
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -377,6 +390,7 @@ def run_native(args, rank, world, local_rank):
                     "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                     "kernel": "march_pose_kernel<FAN>", "kernel_ms": kernel_ms,
                     "kernel_ms_warm_l2": warm_kernel_ms,
+                    "kernel_ms_flushed_field_pinned": pinned_kernel_ms,
                     "algorithmic_bytes_per_launch": alg_bytes, "march_steps_per_ray": mean_steps / n_rays,
                     "note": "the march is an L2-resident gather, not an HBM stream; l2_gather is the bound "
                             "BASELINE.json names",
@@ -423,7 +437,8 @@ def run_native(args, rank, world, local_rank):
                                        "allgather": ", NCCL all_gather of ranges inside the step",
                                        "p2p": ", ranges stored into every GPU's gathered buffer over NVLink by the march "
                                               "kernel (fused all-gather) + 4-byte all_reduce as barrier, inside the step"}[mode],
-                       "l2": "no flush" if args.no_flush else "flushed between steps (256 MiB fill), fill excluded from the per-step events",
+                       "l2": "no flush" if args.no_flush else "flushed between steps (256 MiB fill + cudaCtxResetPersistingL2Cache, so the "
+                             "distance field the product pins in L2 is evicted too), excluded from the per-step events",
                        "timing": "CUDA events per step on the launching stream, summed, max over ranks",
                        "trig": "exact: glibc's sinf/cosf algorithm evaluated per beam on the device (bit parity with the host libm)"},
             "wall_ms_per_step_incl_flush": t_wall / K * 1e3,

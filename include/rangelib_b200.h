@@ -217,6 +217,11 @@ RL_API int32_t rl_follow_gap(const float *d_scans, int64_t num_scans, int32_t nu
 RL_API int32_t rl_gather_bandwidth(int32_t device, int64_t buffer_bytes, int32_t rounds, int32_t iters,
                                    float *gbytes_per_s);
 
+/* Demote all persisting L2 lines to normal.  The march launches pin the distance field in L2 with an  */
+/* access-policy window (it survives unrelated traffic between calls); a benchmark that wants a truly  */
+/* cold cache calls this together with its L2 flush.                                                  */
+RL_API int32_t rl_l2_reset_persisting(int32_t device);
+
 /* The device's sinf/cosf (glibc's algorithm, csrc/glibc_trig.cuh) over an array on the      */
 /* current device, for the parity tests: d_sin[i] = sinf(d_in[i]), d_cos[i] = cosf(d_in[i]). */
 RL_API int32_t rl_probe_sincosf(const float *d_in, float *d_sin, float *d_cos, int64_t n, void *stream);

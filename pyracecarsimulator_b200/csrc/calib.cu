@@ -69,3 +69,14 @@ extern "C" RL_API int32_t rl_gather_bandwidth(int32_t device, int64_t buffer_byt
     *gbytes_per_s = (float)(gathers * 4.0 / (ms * 1e-3) / 1e9);
     return RL_OK;
 }
+
+// Demote every persisting L2 line of the current context to normal (cudaCtxResetPersistingL2Cache), so
+// that a benchmark's L2 flush also evicts the distance field the march launches pin with their
+// access-policy window.
+extern "C" RL_API int32_t rl_l2_reset_persisting(int32_t device)
+{
+    rl::DeviceGuard guard(device);
+    if (!guard.ok) return rl::fail(RL_ERR_NO_DEVICE, "rl_l2_reset_persisting: bad device");
+    RL_CUDA(cudaCtxResetPersistingL2Cache());
+    return RL_OK;
+}

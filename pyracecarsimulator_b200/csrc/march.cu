@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <utility>
 
 #include "glibc_trig.cuh"
 #include "march.cuh"
@@ -125,6 +126,11 @@ struct rl_marcher {
     cudaStream_t stream = nullptr, stream2 = nullptr;   // double-buffered H2D -> march -> D2H pipeline
     float *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr, *d_angles = nullptr;
     size_t cap_in = 0, cap_out = 0, cap_angles = 0;  // floats
+    // L2 persistence: the distance field is the one buffer every ray of every call re-reads, so each march
+    // launch carries an access-policy window over it (persisting hits) and it stays L2-resident between
+    // calls whatever else streams through the cache (0 = window unavailable on this device)
+    size_t l2_window_bytes = 0;
+    float l2_hit_ratio = 1.0f;
     // optional step counter
     bool count = false;
     unsigned long long *d_steps = nullptr;
@@ -157,13 +163,39 @@ bool is_pinned(const void *p)
     return a.type == cudaMemoryTypeHost;
 }
 
+// Launch with the distance-field access-policy window attached to this launch only (no stream or
+// device state of the caller is touched beyond the persisting-L2 carve-out set at marcher creation).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_windowed(const rl_marcher *m, void (*kernel)(KArgs...), unsigned blocks, cudaStream_t s,
+                            Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(CTA_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    if (m->l2_window_bytes) {
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = const_cast<float *>(m->P.dist);
+        attr[0].val.accessPolicyWindow.num_bytes = m->l2_window_bytes;
+        attr[0].val.accessPolicyWindow.hitRatio = m->l2_hit_ratio;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 int32_t launch_many(rl_marcher *m, const float *d_ins, float *d_outs, int64_t n, cudaStream_t s)
 {
     if (n == 0) return RL_OK;
     const int64_t blocks = (n + CTA_THREADS - 1) / CTA_THREADS;
     if (blocks > 0x7fffffffLL) return rl::fail(RL_ERR_BAD_ARG, "calc_range_many: too many rays for one call");
-    if (m->count) march_many_kernel<true><<<(unsigned)blocks, CTA_THREADS, 0, s>>>(m->P, d_ins, d_outs, n, m->d_steps);
-    else march_many_kernel<false><<<(unsigned)blocks, CTA_THREADS, 0, s>>>(m->P, d_ins, d_outs, n, nullptr);
+    unsigned long long *ctr = m->count ? m->d_steps : nullptr;
+    if (m->count) RL_CUDA(launch_windowed(m, march_many_kernel<true>, (unsigned)blocks, s, m->P, d_ins, d_outs, n, ctr));
+    else RL_CUDA(launch_windowed(m, march_many_kernel<false>, (unsigned)blocks, s, m->P, d_ins, d_outs, n, ctr));
     RL_CUDA(cudaGetLastError());
     return RL_OK;
 }
@@ -192,9 +224,11 @@ int32_t launch_pose(rl_marcher *m, const float *d_poses, int64_t stride_rows, co
     const float inc = fov / (float)num_beams;   // IEEE division, same bits as the oracle's
     const bool small = num_beams >= 2 && total < ((int64_t)1 << 31);
     unsigned long long *ctr = m->count ? m->d_steps : nullptr;
+    const int64_t stride_floats = stride_rows * 3;
+    const PeerOut no_peers{};
 #define RL_LAUNCH(COUNT, SMALL)                                                                    \
-    march_pose_kernel<FAN, COUNT, SMALL><<<(unsigned)blocks, CTA_THREADS, 0, s>>>(                   \
-        m->P, d_poses, stride_rows * 3, d_angles, d_outs, total, num_beams, div, fov, inc, ctr)
+    RL_CUDA(launch_windowed(m, march_pose_kernel<FAN, COUNT, SMALL, false>, (unsigned)blocks, s, m->P, d_poses, \
+                            stride_floats, d_angles, d_outs, total, num_beams, div, fov, inc, ctr, no_peers))
     if (m->count) { if (small) RL_LAUNCH(true, true); else RL_LAUNCH(true, false); }
     else { if (small) RL_LAUNCH(false, true); else RL_LAUNCH(false, false); }
 #undef RL_LAUNCH
@@ -316,6 +350,21 @@ int32_t rl_marcher_create(const rl_map *map, float max_range_px, uint32_t flags,
     m->P.max_range = max_range_px;
     m->P.w = map->world;
     cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, map->device);
+    {   // persisting-L2 carve-out large enough for the distance field (device-wide limit; only ever raised)
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, map->device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, map->device);
+        const size_t field = (size_t)map->rows * map->cols * sizeof(float);
+        size_t cur = 0;
+        cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
+        // only when the whole field fits: pinning a fraction of a larger field measured slightly slower
+        if (max_persist > 0 && field <= (size_t)max_persist && field <= (size_t)max_window &&
+            (cur >= field || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, field) == cudaSuccess)) {
+            m->l2_window_bytes = field;
+            m->l2_hit_ratio = 1.0f;
+        }
+        cudaGetLastError();
+    }
     cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&m->d_steps, sizeof(unsigned long long));
@@ -461,12 +510,16 @@ int32_t rl_calc_range_fan_allgather(rl_marcher *m, const float *d_poses, int64_t
     const rl::FastDiv div = make_fast_div(num_rays);
     const float inc = fov / (float)num_rays;
     cudaStream_t s = (cudaStream_t)stream;
+    const int64_t stride_floats = pose_stride_rows * 3;
+    const float *no_angles = nullptr;
+    float *no_outs = nullptr;
+    unsigned long long *no_ctr = nullptr;
     if (num_rays >= 2 && total < ((int64_t)1 << 31))
-        march_pose_kernel<true, false, true, true><<<(unsigned)blocks, CTA_THREADS, 0, s>>>(
-            m->P, d_poses, pose_stride_rows * 3, nullptr, nullptr, total, num_rays, div, fov, inc, nullptr, po);
+        RL_CUDA(launch_windowed(m, march_pose_kernel<true, false, true, true>, (unsigned)blocks, s, m->P, d_poses,
+                                stride_floats, no_angles, no_outs, total, (int)num_rays, div, fov, inc, no_ctr, po));
     else
-        march_pose_kernel<true, false, false, true><<<(unsigned)blocks, CTA_THREADS, 0, s>>>(
-            m->P, d_poses, pose_stride_rows * 3, nullptr, nullptr, total, num_rays, div, fov, inc, nullptr, po);
+        RL_CUDA(launch_windowed(m, march_pose_kernel<true, false, false, true>, (unsigned)blocks, s, m->P, d_poses,
+                                stride_floats, no_angles, no_outs, total, (int)num_rays, div, fov, inc, no_ctr, po));
     RL_CUDA(cudaGetLastError());
     return RL_OK;
 }
