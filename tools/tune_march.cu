@@ -2,6 +2,7 @@
 // candidate fan-march kernel structures on the same distance field and poses, checks every
 // candidate bit-for-bit against the straightforward one, and prints a table.
 //   python tools/tune_prep.py /tmp/tune && tools/tune_march /tmp/tune [reps]
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -735,6 +736,104 @@ __global__ void __launch_bounds__(128) k_pstatic(Args a, Lean q, unsigned static
     }
 }
 
+// ---------------------------------------------------------------- V17: the product loop with an interior variant
+// (poses >= max_range + 1 px from every border skip the bounds tests: 13 instead of 16 instructions per step).
+// Measured 86.1 vs 84.8 us: no gain, the loop is bound by load latency, not by issue slots -- not adopted.
+// The loop after the first sample.  CHECK = false is the interior variant: the caller has proved that no
+// sample with t < max_range can leave the map, so the two bounds compares and their branch (3 of the 16
+// instructions of a step) are compiled out.  Same samples, same arithmetic, same result.
+template <bool COUNT, bool CHECK>
+__device__ __forceinline__ float march_loop(const MarchParams &P, float x0, float y0, float dx, float dy,
+                                            float t, uint32_t &steps)
+{
+    // One exit branch per step: t is advanced before the hit test (harmless: a hit ends the ray) and
+    // which of the two exits it was is decided once, after the loop.
+    int px, py, it = 1;
+    float d;
+    bool tail = false;
+    for (;;) {
+        px = __float2int_rz(fmaf(dx, t, x0));
+        py = __float2int_rz(fmaf(dy, t, y0));
+        if (CHECK && ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols)) return P.max_range;
+        d = __ldg(P.dist + (px * P.cols + py));
+        if (COUNT) ++steps;
+        t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+        if (d <= 0.0f || !(t < P.max_range)) break;
+        if (++it == rl::TAIL_AFTER) { tail = true; break; }
+    }
+    if (tail) {
+        float j0 = 0.f, j1 = 0.f, j2 = 0.f, j3 = 0.f, keep = 0.f;
+        const float adx = __fmul_rn(dx, (float)rl::TAIL_AHEAD), ady = __fmul_rn(dy, (float)rl::TAIL_AHEAD);
+        bool inside = true;
+#define RL_TAIL_STEP(J)                                                                            \
+        {                                                                                          \
+            const float fx = fmaf(dx, t, x0), fy = fmaf(dy, t, y0);                                \
+            px = __float2int_rz(fx);                                                               \
+            py = __float2int_rz(fy);                                                               \
+            if (CHECK && ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols)) { inside = false; break; } \
+            d = __ldg(P.dist + (px * P.cols + py));                                                \
+            if (COUNT) ++steps;                                                                    \
+            const int ax = __float2int_rz(__fadd_rn(fx, adx)), ay = __float2int_rz(__fadd_rn(fy, ady)); \
+            keep = __fadd_rn(keep, J);                                                             \
+            if ((unsigned)ax < (unsigned)P.rows && (unsigned)ay < (unsigned)P.cols)                \
+                asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(J) : "l"(P.dist + (ax * P.cols + ay))); \
+            t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));                                   \
+            if (d <= 0.0f || !(t < P.max_range)) break;                                            \
+        }
+        for (;;) { RL_TAIL_STEP(j0) RL_TAIL_STEP(j1) RL_TAIL_STEP(j2) RL_TAIL_STEP(j3) }
+#undef RL_TAIL_STEP
+        if (__fadd_rn(__fadd_rn(keep, j0), __fadd_rn(j1, __fadd_rn(j2, j3))) < 0.0f) return -1.0f;  // never true
+        if (!inside) return P.max_range;
+    }
+    if (d <= 0.0f) {
+        const float xd = __fsub_rn((float)px, x0);
+        const float yd = __fsub_rn((float)py, y0);
+        return sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+    }
+    return P.max_range;
+}
+
+// Interior test: |dx|, |dy| <= 1 (they are sinf/cosf values), so a sample at parameter t < max_range lies
+// within max_range (plus a rounding error far below the 1 px margin) of the pose along each axis.  A pose
+// at least max_range + 1 px from every border of the map can therefore never produce an out-of-map sample
+// and its rays take the loop without bounds tests.  The decision depends on the pose only, so the warps of
+// a pose (almost all warps: one warp rarely straddles two poses) stay convergent.
+__device__ __forceinline__ bool pose_is_interior(const MarchParams &P, float x0, float y0)
+{
+    const float margin = fminf(fminf(x0, y0), fminf(__fsub_rn(P.frows, x0), __fsub_rn(P.fcols, y0)));
+    return __fsub_rn(margin, 1.0f) >= P.max_range;   // false for NaN
+}
+
+template <bool COUNT, bool INTERIOR_PATH>
+__device__ __forceinline__ float march_ray_v17(const MarchParams &P, float x0, float y0, float dx,
+                                           float dy, uint32_t &steps, const rl::FirstSample &f0)
+{
+    if (!f0.inside || !(dx == dx) || !(dy == dy)) return P.max_range;   // NaN pose/heading or pose outside the map
+    if (COUNT) ++steps;
+    if (f0.d <= 0.0f) {   // pose inside an occupied cell: distance to that cell's corner
+        const float xd = __fsub_rn((float)f0.px, x0);
+        const float yd = __fsub_rn((float)f0.py, y0);
+        return sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+    }
+    const float t = fmaxf(__fmul_rn(f0.d, 0.999f), 1.0f);   // 0 + step
+    if (!(t < P.max_range)) return P.max_range;
+    if (INTERIOR_PATH && pose_is_interior(P, x0, y0)) return march_loop<COUNT, false>(P, x0, y0, dx, dy, t, steps);
+    return march_loop<COUNT, true>(P, x0, y0, dx, dy, t, steps);
+}
+
+template <bool INTERIOR>
+__global__ void __launch_bounds__(128) k_product_like_t(Args a, Lean q)
+{
+    const unsigned i = blockIdx.x * 128u + threadIdx.x;
+    const unsigned total = (unsigned)a.num_poses * a.num_beams;
+    if (i >= total) return;
+    float x0, y0, dx, dy;
+    ray_setup_fan(a, q, i, x0, y0, dx, dy);
+    const rl::FirstSample f0 = rl::first_sample(a.P, x0, y0);
+    uint32_t st = 0;
+    a.outs[i] = __fmul_rn(march_ray_v17<false, INTERIOR>(a.P, x0, y0, dx, dy, st, f0), a.P.w.scale);
+}
+
 __global__ void __launch_bounds__(128) k_product_like(Args a, Lean q)
 {
     const unsigned i = blockIdx.x * 128u + threadIdx.x;
@@ -952,6 +1051,523 @@ __global__ void __launch_bounds__(128) k_spec2(Args a, Lean q)
     a.outs[i] = __fmul_rn(r, P.w.scale);
 }
 
+// ---------------------------------------------------------------- V16 (round 1, second session): three ideas on top of
+// the product loop, separately switchable.
+//  SAFE : a conservative t_safe below which no sample can leave the map (|dx|,|dy| <= 1, so a ray is still
+//         >= 1 px inside every border while t < min(x0, y0, rows-x0, cols-y0) - 1): steps below it skip the two
+//         bounds compares + branch (3 of 16 instructions per step).
+//  COOP : after COOP steps in lockstep the lanes whose rays are still marching are served by the whole
+//         warp: 32/m lanes per surviving ray sample t, t+s, t+2s, ... (s = the ray's previous step), a ballot
+//         finds how far the "same step again" prediction held, and the ray advances that many steps in one
+//         memory round trip.  Same t sequence bit for bit (each lane adds s sequentially).
+//  PERSIST: persistent CTAs; a warp takes CH consecutive 32-ray groups per global atomic (CH = 1 for the
+//         last part of the batch), so all 64 warp slots of an SM stay busy and L1 locality is kept.
+struct RayState { float x0, y0, dx, dy, t, d; int px, py; int st; };   // st 0 running, 1 hit at (px,py), 2 max range
+
+template <bool SAFE, int LIMIT>
+__device__ __forceinline__ void march_limited(const MarchParams &P, RayState &r)
+{
+    // first sample (t = 0)
+    r.st = 2; r.t = 0.f; r.d = 1.f; r.px = 0; r.py = 0;
+    if (!((r.x0 == r.x0) && (r.y0 == r.y0) && (r.dx == r.dx) && (r.dy == r.dy))) return;
+    int px = __float2int_rz(r.x0), py = __float2int_rz(r.y0);
+    if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) return;
+    float d = __ldg(P.dist + (px * P.cols + py));
+    if (d <= 0.0f) { r.st = 1; r.px = px; r.py = py; return; }
+    float t = fmaxf(__fmul_rn(d, 0.999f), 1.0f);
+    if (!(t < P.max_range)) return;
+    int it = 1;
+    if (SAFE) {
+        const float t_safe = __fadd_rn(fminf(fminf(r.x0, r.y0), fminf(__fsub_rn(P.frows, r.x0), __fsub_rn(P.fcols, r.y0))), -1.0f);
+        const float t_lim = fminf(t_safe, P.max_range);
+        if (t < t_lim) {
+            for (;;) {
+                px = __float2int_rz(fmaf(r.dx, t, r.x0));
+                py = __float2int_rz(fmaf(r.dy, t, r.y0));
+                d = __ldg(P.dist + (px * P.cols + py));
+                t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+                if (d <= 0.0f) { r.st = 1; r.px = px; r.py = py; return; }
+                if (!(t < t_lim)) break;
+                if (++it == LIMIT) { r.st = 0; r.t = t; r.d = d; return; }
+            }
+            if (!(t < P.max_range)) return;
+            if (++it == LIMIT) { r.st = 0; r.t = t; r.d = d; return; }
+        }
+    }
+    for (;;) {
+        px = __float2int_rz(fmaf(r.dx, t, r.x0));
+        py = __float2int_rz(fmaf(r.dy, t, r.y0));
+        if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) return;
+        d = __ldg(P.dist + (px * P.cols + py));
+        t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+        if (d <= 0.0f) { r.st = 1; r.px = px; r.py = py; return; }
+        if (!(t < P.max_range)) return;
+        if (++it == LIMIT) { r.st = 0; r.t = t; r.d = d; return; }
+    }
+}
+
+// plain continuation (no cooperation): checked loop with the product's look-ahead touches
+__device__ __forceinline__ void march_rest_plain(const MarchParams &P, RayState &r)
+{
+    float t = r.t, d;
+    int px, py;
+    float j0 = 0.f, j1 = 0.f, j2 = 0.f, j3 = 0.f, keep = 0.f;
+    const float adx = __fmul_rn(r.dx, 12.0f), ady = __fmul_rn(r.dy, 12.0f);
+#define V16_STEP(J)                                                                                \
+    {                                                                                              \
+        const float fx = fmaf(r.dx, t, r.x0), fy = fmaf(r.dy, t, r.y0);                            \
+        px = __float2int_rz(fx); py = __float2int_rz(fy);                                          \
+        if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) { r.st = 2; break; } \
+        d = __ldg(P.dist + (px * P.cols + py));                                                    \
+        const int ax = __float2int_rz(__fadd_rn(fx, adx)), ay = __float2int_rz(__fadd_rn(fy, ady)); \
+        keep = __fadd_rn(keep, J);                                                                 \
+        if ((unsigned)ax < (unsigned)P.rows && (unsigned)ay < (unsigned)P.cols)                    \
+            asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(J) : "l"(P.dist + (ax * P.cols + ay))); \
+        t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));                                       \
+        if (d <= 0.0f) { r.st = 1; r.px = px; r.py = py; break; }                                  \
+        if (!(t < P.max_range)) { r.st = 2; break; }                                               \
+    }
+    for (;;) { V16_STEP(j0) V16_STEP(j1) V16_STEP(j2) V16_STEP(j3) }
+#undef V16_STEP
+    if (__fadd_rn(__fadd_rn(keep, j0), __fadd_rn(j1, __fadd_rn(j2, j3))) < 0.0f) r.st = 3;   // never true
+}
+
+// warp-cooperative continuation.  Must be called by all 32 lanes; `unfinished` = this lane's ray is running
+// (r.t = parameter of its next sample, < max_range; r.d = clearance of its previous sample, > 0).
+__device__ __forceinline__ void march_rest_coop(const MarchParams &P, RayState &r, bool unfinished)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned m = __ballot_sync(0xffffffffu, unfinished);
+    while (m) {
+        const int ma = __popc(m);
+        const int lg = ma <= 1 ? 0 : 32 - __clz(ma - 1);   // ceil(log2(ma)), 0..5
+        const int G = 32 >> lg;                            // lanes per served ray
+        const int g = lane >> (5 - lg);                    // group of this lane
+        const int k = lane & (G - 1);                      // position in the group
+        const bool has = g < ma;
+        const int owner = has ? (int)__fns(m, 0, g + 1) : 0;
+        const float ox0 = __shfl_sync(0xffffffffu, r.x0, owner), oy0 = __shfl_sync(0xffffffffu, r.y0, owner);
+        const float odx = __shfl_sync(0xffffffffu, r.dx, owner), ody = __shfl_sync(0xffffffffu, r.dy, owner);
+        const float ot = __shfl_sync(0xffffffffu, r.t, owner), od = __shfl_sync(0xffffffffu, r.d, owner);
+        const float s = fmaxf(__fmul_rn(od, 0.999f), 1.0f);
+        float tk = ot;
+        for (int j = 1; j < G; ++j) tk = (j <= k) ? __fadd_rn(tk, s) : tk;
+        // sample k of the group
+        const int px = __float2int_rz(fmaf(odx, tk, ox0)), py = __float2int_rz(fmaf(ody, tk, oy0));
+        const bool live = tk < P.max_range;    // lane 0: true by invariant
+        const bool inb = (unsigned)px < (unsigned)P.rows && (unsigned)py < (unsigned)P.cols;
+        float d = 1.0f;
+        if (has && live && inb) d = __ldg(P.dist + (px * P.cols + py));
+        const float sk = fmaxf(__fmul_rn(d, 0.999f), 1.0f);
+        const bool good = live && inb && d > 0.0f && sk == s;           // the next lane's position is right
+        const unsigned bad = __ballot_sync(0xffffffffu, !good);
+        const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (g * G);
+        const unsigned gb = bad & gmask;
+        const int f = gb ? (__ffs(gb) - 1) : (g * G + G - 1);           // lane that decides the ray's new state
+        // state as seen by the deciding lane
+        int st = 0; float nt = __fadd_rn(tk, sk), nd = d;
+        if (!live) st = 2;
+        else if (!inb) st = 2;
+        else if (d <= 0.0f) st = 1;
+        else if (!(nt < P.max_range)) st = 2;
+        // ship it to the owner: the owner lane reads from lane f of ITS group
+        // (owner's group index = rank of the owner among the set bits of m)
+        const int myrank = __popc(m & ((1u << lane) - 1u));
+        const unsigned gmask_o = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (myrank * G);
+        const unsigned gb_o = bad & gmask_o;
+        const int src = unfinished ? (gb_o ? (__ffs(gb_o) - 1) : (myrank * G + G - 1)) : (int)lane;
+        const int st_o = __shfl_sync(0xffffffffu, st, src);
+        const float nt_o = __shfl_sync(0xffffffffu, nt, src), nd_o = __shfl_sync(0xffffffffu, nd, src);
+        const int px_o = __shfl_sync(0xffffffffu, px, src), py_o = __shfl_sync(0xffffffffu, py, src);
+        (void)f;
+        if (unfinished) {
+            r.st = st_o; r.t = nt_o; r.d = nd_o; r.px = px_o; r.py = py_o;
+            unfinished = st_o == 0;
+        }
+        m = __ballot_sync(0xffffffffu, unfinished);
+    }
+}
+
+__device__ __forceinline__ float ray_result(const MarchParams &P, const RayState &r)
+{
+    if (r.st == 1) {
+        const float xd = __fsub_rn((float)r.px, r.x0), yd = __fsub_rn((float)r.py, r.y0);
+        return sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+    }
+    return r.st == 3 ? -1.0f : P.max_range;
+}
+
+template <bool SAFE, int COOP>   // COOP = 0: plain continuation after 32 steps (product behaviour)
+__global__ void __launch_bounds__(128) k_v16(Args a, Lean q)
+{
+    const unsigned i = blockIdx.x * 128u + threadIdx.x;
+    const unsigned total = (unsigned)a.num_poses * a.num_beams;
+    const bool valid = i < total;
+    RayState r;
+    bool unfinished = false;
+    if (valid) {
+        ray_setup_fan(a, q, i, r.x0, r.y0, r.dx, r.dy);
+        march_limited<SAFE, COOP ? COOP : 32>(a.P, r);
+        unfinished = r.st == 0;
+    }
+    if (COOP) march_rest_coop(a.P, r, unfinished);
+    else if (unfinished) march_rest_plain(a.P, r);
+    if (valid) a.outs[i] = __fmul_rn(ray_result(a.P, r), a.P.w.scale);
+}
+
+template <bool SAFE, int COOP, int CH>
+__global__ void __launch_bounds__(128, 16) k_v16p(Args a, Lean q, unsigned ngroups, unsigned chunked_groups)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned total = (unsigned)a.num_poses * a.num_beams;
+    const unsigned nchunks = chunked_groups / CH;    // chunked_groups is a multiple of CH
+    unsigned v = 0;
+    if (lane == 0) v = atomicAdd(a.counter, 1u);
+    v = __shfl_sync(0xffffffffu, v, 0);
+    for (;;) {
+        unsigned g0, g1;
+        if (v < nchunks) { g0 = v * CH; g1 = g0 + CH; }
+        else { g0 = chunked_groups + (v - nchunks); g1 = g0 + 1; }
+        if (g0 >= ngroups) break;
+        // fetch the next ticket now; it is needed only after this chunk
+        unsigned vn = 0;
+        if (lane == 0) vn = atomicAdd(a.counter, 1u);
+        for (unsigned g = g0; g < g1; ++g) {
+            const unsigned i = g * 32u + lane;
+            const bool valid = i < total;
+            RayState r;
+            bool unfinished = false;
+            if (valid) {
+                ray_setup_fan(a, q, i, r.x0, r.y0, r.dx, r.dy);
+                march_limited<SAFE, COOP ? COOP : 32>(a.P, r);
+                unfinished = r.st == 0;
+            }
+            if (COOP) march_rest_coop(a.P, r, unfinished);
+            else if (unfinished) march_rest_plain(a.P, r);
+            if (valid) a.outs[i] = __fmul_rn(ray_result(a.P, r), a.P.w.scale);
+            __syncwarp();
+        }
+        v = __shfl_sync(0xffffffffu, vn, 0);
+    }
+}
+
+// ---------------------------------------------------------------- V18: memory-level parallelism.  The march is a chain
+// of dependent loads and a warp has one of them in flight; with the register file full at 32 registers x 2048
+// threads the only way to more loads in flight per SM is R rays per thread that share the pose (x0, y0), marched
+// in lockstep with their R loads issued back to back.  A warp takes 32*R consecutive beams of ONE pose
+// (chunks_per_pose = ceil(beams / 32R)); rays still marching after 32 lockstep steps finish one after another
+// through the product's look-ahead loop.
+template <int R>
+__global__ void __launch_bounds__(128) k_mlp(Args a, Lean q, unsigned chunks_per_pose, unsigned cmagic, unsigned cshift)
+{
+    const MarchParams &P = a.P;
+    const unsigned w = (blockIdx.x * 128u + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    const unsigned k = chunks_per_pose == 1 ? w : (__umulhi(w, cmagic) >> cshift);
+    if (k >= (unsigned)a.num_poses) return;
+    const unsigned c = w - k * chunks_per_pose;
+    const float *p = a.poses + 3 * k;
+    const float thw = __ldg(p + 2);
+    const GridPose g = rl::world_to_grid(P.w, __ldg(p), __ldg(p + 1), thw);
+    const float x0 = g.y, y0 = g.x;
+    const rl::FirstSample f0 = rl::first_sample(P, x0, y0);
+    const int jb = (int)(c * 32u * R + lane);
+    float dx[R], dy[R], t[R], res[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int j = jb + 32 * r;
+        const float thg = __fadd_rn(-__fadd_rn(thw, fmaf((float)j, q.inc, -0.5f * a.fov)), P.w.rotation_const);
+        rl::glibc_sincosf(thg, &dy[r], &dx[r]);
+        res[r] = P.max_range;
+    }
+    const float INF = __int_as_float(0x7f800000);
+    float t_first = INF;
+    if (f0.inside) {
+        if (f0.d <= 0.0f) {
+            const float xd = __fsub_rn((float)f0.px, x0), yd = __fsub_rn((float)f0.py, y0);
+            const float r0 = sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+#pragma unroll
+            for (int r = 0; r < R; ++r) if ((dx[r] == dx[r]) && (dy[r] == dy[r])) res[r] = r0;
+        } else {
+            t_first = fmaxf(__fmul_rn(f0.d, 0.999f), 1.0f);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const bool ok = (dx[r] == dx[r]) && (dy[r] == dy[r]) && (jb + 32 * r < a.num_beams);
+        t[r] = ok ? t_first : INF;     // t >= max_range (or INF) = finished
+    }
+    int it = 1;
+    for (;;) {
+        bool live[R];
+        bool any = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) { live[r] = t[r] < P.max_range; any |= live[r]; }
+        if (!any) break;
+        if (it == 32) break;
+        ++it;
+        int px[R], py[R];
+        float d[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            px[r] = __float2int_rz(fmaf(dx[r], t[r], x0));
+            py[r] = __float2int_rz(fmaf(dy[r], t[r], y0));
+            const bool inb = (unsigned)px[r] < (unsigned)P.rows && (unsigned)py[r] < (unsigned)P.cols;
+            d[r] = 1.0f;
+            if (live[r] && !inb) { t[r] = INF; live[r] = false; }
+            if (live[r]) d[r] = __ldg(P.dist + (px[r] * P.cols + py[r]));
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (live[r]) {
+                if (d[r] <= 0.0f) {
+                    const float xd = __fsub_rn((float)px[r], x0), yd = __fsub_rn((float)py[r], y0);
+                    res[r] = sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+                    t[r] = INF;
+                } else {
+                    t[r] = __fadd_rn(t[r], fmaxf(__fmul_rn(d[r], 0.999f), 1.0f));
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (t[r] < P.max_range) {      // still marching after 32 steps: the product's tail loop
+            RayState s;
+            s.x0 = x0; s.y0 = y0; s.dx = dx[r]; s.dy = dy[r]; s.t = t[r]; s.d = 1.f; s.px = 0; s.py = 0; s.st = 0;
+            march_rest_plain(P, s);
+            res[r] = ray_result(P, s);
+        }
+    }
+    float *o = a.outs + (size_t)k * a.num_beams;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int j = jb + 32 * r;
+        if (j < a.num_beams) o[j] = __fmul_rn(res[r], P.w.scale);
+    }
+}
+
+// ---------------------------------------------------------------- diag2: the PRODUCT march (tail mode included) with
+// per-warp start/end stamps and per-ray cycle counts, to see what the end of the kernel consists of now.
+struct Diag2 { unsigned long long *t_first, *t_last; unsigned *max_steps; unsigned *ray_steps; unsigned *ray_cycles; };
+
+__global__ void __launch_bounds__(128) k_diag2(Args a, Lean q, Diag2 D)
+{
+    const unsigned i = blockIdx.x * 128u + threadIdx.x;
+    const unsigned total = (unsigned)a.num_poses * a.num_beams;
+    if (i >= total) return;
+    const unsigned long long tstart = gtime();
+    float x0, y0, dx, dy;
+    ray_setup_fan(a, q, i, x0, y0, dx, dy);
+    const rl::FirstSample f0 = rl::first_sample(a.P, x0, y0);
+    uint32_t st = 0;
+    const long long c0 = clock64();
+    a.outs[i] = __fmul_rn(rl::march_ray<true>(a.P, x0, y0, dx, dy, st, f0), a.P.w.scale);
+    const long long c1 = clock64();
+    D.ray_steps[i] = st;
+    D.ray_cycles[i] = (unsigned)(c1 - c0);
+    const unsigned long long tend = gtime();
+    D.t_first[i >> 5] = tstart;
+    atomicMax(D.t_last + (i >> 5), tend);
+    atomicMax(D.max_steps + (i >> 5), st);
+}
+
+// ---------------------------------------------------------------- V19: the product march with the tail touch aimed
+// at the PREDICTED sample K steps ahead (t + K * s, s = the step just taken) instead of a fixed 12 px ahead:
+// long rays creep along walls with the same clearance for 10-20 steps in a row, so the touched cell is the
+// very cell the ray will sample K steps later (a fixed distance ahead falls between samples and, for rays
+// that cross rows, into a different sector).  Touches never influence the result.
+template <int AFTER, int K>
+__device__ __forceinline__ float march_ray_v19(const MarchParams &P, float x0, float y0, float dx, float dy,
+                                               const rl::FirstSample &f0)
+{
+    if (!f0.inside || !(dx == dx) || !(dy == dy)) return P.max_range;
+    if (f0.d <= 0.0f) {
+        const float xd = __fsub_rn((float)f0.px, x0), yd = __fsub_rn((float)f0.py, y0);
+        return sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+    }
+    float t = fmaxf(__fmul_rn(f0.d, 0.999f), 1.0f);
+    if (!(t < P.max_range)) return P.max_range;
+    int px, py, it = 1;
+    float d;
+    bool tail = false;
+    for (;;) {
+        px = __float2int_rz(fmaf(dx, t, x0));
+        py = __float2int_rz(fmaf(dy, t, y0));
+        if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) return P.max_range;
+        d = __ldg(P.dist + (px * P.cols + py));
+        t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+        if (d <= 0.0f || !(t < P.max_range)) break;
+        if (++it == AFTER) { tail = true; break; }
+    }
+    if (tail) {
+        float j0 = 0.f, j1 = 0.f, j2 = 0.f, j3 = 0.f, keep = 0.f;
+        float s = fmaxf(__fmul_rn(d, 0.999f), 1.0f);
+        bool inside = true;
+#define V19_STEP(J)                                                                                \
+        {                                                                                          \
+            px = __float2int_rz(fmaf(dx, t, x0));                                                  \
+            py = __float2int_rz(fmaf(dy, t, y0));                                                  \
+            if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) { inside = false; break; } \
+            d = __ldg(P.dist + (px * P.cols + py));                                                \
+            const float tt = fmaf((float)K, s, t);                                                 \
+            const int ax = __float2int_rz(fmaf(dx, tt, x0)), ay = __float2int_rz(fmaf(dy, tt, y0)); \
+            keep = __fadd_rn(keep, J);                                                             \
+            if ((unsigned)ax < (unsigned)P.rows && (unsigned)ay < (unsigned)P.cols)                \
+                asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(J) : "l"(P.dist + (ax * P.cols + ay))); \
+            s = fmaxf(__fmul_rn(d, 0.999f), 1.0f);                                                 \
+            t = __fadd_rn(t, s);                                                                   \
+            if (d <= 0.0f || !(t < P.max_range)) break;                                            \
+        }
+        for (;;) { V19_STEP(j0) V19_STEP(j1) V19_STEP(j2) V19_STEP(j3) }
+#undef V19_STEP
+        if (__fadd_rn(__fadd_rn(keep, j0), __fadd_rn(j1, __fadd_rn(j2, j3))) < 0.0f) return -1.0f;  // never true
+        if (!inside) return P.max_range;
+    }
+    if (d <= 0.0f) {
+        const float xd = __fsub_rn((float)px, x0), yd = __fsub_rn((float)py, y0);
+        return sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+    }
+    return P.max_range;
+}
+
+template <int AFTER, int K>
+__global__ void __launch_bounds__(128) k_v19(Args a, Lean q)
+{
+    const unsigned i = blockIdx.x * 128u + threadIdx.x;
+    const unsigned total = (unsigned)a.num_poses * a.num_beams;
+    if (i >= total) return;
+    float x0, y0, dx, dy;
+    ray_setup_fan(a, q, i, x0, y0, dx, dy);
+    const rl::FirstSample f0 = rl::first_sample(a.P, x0, y0);
+    a.outs[i] = __fmul_rn(march_ray_v19<AFTER, K>(a.P, x0, y0, dx, dy, f0), a.P.w.scale);
+}
+
+// diag3: light-weight stamps only (lane 0 of each warp), product march untouched otherwise
+template <int MODE>   // 0: product march; 1: v19<32,6>
+__global__ void __launch_bounds__(128) k_diag3(Args a, Lean q, unsigned long long *t_first, unsigned long long *t_last)
+{
+    const unsigned i = blockIdx.x * 128u + threadIdx.x;
+    const unsigned total = (unsigned)a.num_poses * a.num_beams;
+    if (i >= total) return;
+    const unsigned long long tstart = gtime();
+    float x0, y0, dx, dy;
+    ray_setup_fan(a, q, i, x0, y0, dx, dy);
+    const rl::FirstSample f0 = rl::first_sample(a.P, x0, y0);
+    uint32_t st = 0;
+    float r;
+    if (MODE == 0) r = rl::march_ray<false>(a.P, x0, y0, dx, dy, st, f0);
+    else r = march_ray_v19<32, 6>(a.P, x0, y0, dx, dy, f0);
+    a.outs[i] = __fmul_rn(r, a.P.w.scale);
+    __syncwarp(__activemask());
+    if ((threadIdx.x & 31) == 0) { t_first[i >> 5] = tstart; t_last[i >> 5] = gtime(); }
+}
+
+// ---------------------------------------------------------------- chain: what one march step costs when nothing else
+// runs.  One warp, `lanes` active rays over a field of constant clearance `dval` (no obstacle, so every ray
+// runs to max_range in steps of max(0.999*dval, 1) px); heading `th0` (+ lane * 0.004 rad).  MODE 0: the plain loop
+// (no touches), 1: the product march (look-ahead touches after 32 steps), 2: v19<32,6>.
+template <int MODE>
+__global__ void k_chain(MarchParams P, float x0, float y0, float th0, int lanes, unsigned *out_steps, long long *out_cycles, float *sink)
+{
+    const int lane = threadIdx.x;
+    if (lane >= lanes) return;
+    float dx, dy;
+    rl::glibc_sincosf(th0 + 0.004f * lane, &dy, &dx);
+    const rl::FirstSample f0 = rl::first_sample(P, x0, y0);
+    uint32_t st = 0;
+    float r;
+    const long long c0 = clock64();
+    if (MODE == 0) {
+        float t = 0.f; r = P.max_range;
+        while (t < P.max_range) {
+            const int px = __float2int_rz(fmaf(dx, t, x0)), py = __float2int_rz(fmaf(dy, t, y0));
+            if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) break;
+            const float d = __ldg(P.dist + (px * P.cols + py));
+            ++st;
+            if (d <= 0.0f) { r = 0.f; break; }
+            t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+        }
+    } else if (MODE == 1) {
+        r = rl::march_ray<true>(P, x0, y0, dx, dy, st, f0);
+    } else {
+        r = march_ray_v19<32, 6>(P, x0, y0, dx, dy, f0);
+        st = 0;
+    }
+    const long long c1 = clock64();
+    sink[lane] = r;
+    out_steps[lane] = st;
+    out_cycles[lane] = c1 - c0;
+}
+
+// ---------------------------------------------------------------- step: latency of one march step with every load an
+// L1 hit (64x64 field of constant clearance, the same ray marched REP times in one launch; the last repetition
+// is timed).  VAR 0: product step (cvt.rzi, integer bounds test, separate out-of-map and exit branches).
+// VAR 1: truncation by a round-down add of 2^23 on max(x, 0) + float bounds test (no cvt in the chain).
+// VAR 2: VAR 0 with the out-of-map test folded into the one exit branch (predicated load).
+// VAR 3: VAR 1 + VAR 2.
+template <int VAR>
+__global__ void k_step(MarchParams P, float x0, float y0, float th0, int reps, long long *out_cycles, unsigned *out_steps, float *sink)
+{
+    float dx, dy;
+    rl::glibc_sincosf(th0, &dy, &dx);
+    float r = 0.f;
+    long long c0 = 0;
+    unsigned st = 0;
+    const int K = -(0x4B000000) * (P.cols + 1);
+    for (int rep = 0; rep < reps; ++rep) {
+        if (rep == reps - 1) { c0 = clock64(); st = 0; }
+        float t = 0.f;
+        r = P.max_range;
+        if (VAR == 0) {
+            for (;;) {
+                const int px = __float2int_rz(fmaf(dx, t, x0)), py = __float2int_rz(fmaf(dy, t, y0));
+                if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) break;
+                const float d = __ldg(P.dist + (px * P.cols + py));
+                ++st;
+                t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+                if (d <= 0.0f || !(t < P.max_range)) { r = d; break; }
+            }
+        } else if (VAR == 1) {
+            for (;;) {
+                const float fx = fmaf(dx, t, x0), fy = fmaf(dy, t, y0);
+                if (!(fx > -1.0f && fx < P.frows && fy > -1.0f && fy < P.fcols)) break;
+                const int bx = __float_as_int(__fadd_rd(fmaxf(fx, 0.0f), 8388608.0f));
+                const int by = __float_as_int(__fadd_rd(fmaxf(fy, 0.0f), 8388608.0f));
+                const float d = __ldg(P.dist + (bx * P.cols + by + K));
+                ++st;
+                t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+                if (d <= 0.0f || !(t < P.max_range)) { r = d; break; }
+            }
+        } else if (VAR == 2) {
+            for (;;) {
+                const int px = __float2int_rz(fmaf(dx, t, x0)), py = __float2int_rz(fmaf(dy, t, y0));
+                const bool inb = (unsigned)px < (unsigned)P.rows && (unsigned)py < (unsigned)P.cols;
+                float d = 0.0f;
+                if (inb) d = __ldg(P.dist + (px * P.cols + py));
+                ++st;
+                t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+                if (d <= 0.0f || !(t < P.max_range)) { r = inb ? d : P.max_range; break; }
+            }
+        } else {
+            for (;;) {
+                const float fx = fmaf(dx, t, x0), fy = fmaf(dy, t, y0);
+                const bool inb = fx > -1.0f && fx < P.frows && fy > -1.0f && fy < P.fcols;
+                const int bx = __float_as_int(__fadd_rd(fmaxf(fx, 0.0f), 8388608.0f));
+                const int by = __float_as_int(__fadd_rd(fmaxf(fy, 0.0f), 8388608.0f));
+                float d = 0.0f;
+                if (inb) d = __ldg(P.dist + (bx * P.cols + by + K));
+                ++st;
+                t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+                if (d <= 0.0f || !(t < P.max_range)) { r = inb ? d : P.max_range; break; }
+            }
+        }
+    }
+    const long long c1 = clock64();
+    sink[0] = r;
+    out_cycles[0] = c1 - c0;
+    out_steps[0] = st;
+}
+
 // ---------------------------------------------------------------- harness
 static std::vector<char> slurp(const std::string &path)
 {
@@ -1079,6 +1695,197 @@ int main(int argc, char **argv)
         auto nb = [&](int bs, int rpl) { return (unsigned)((R.n_rays + (size_t)bs * rpl - 1) / ((size_t)bs * rpl)); };
         if (ok) {
         unsigned b3 = (unsigned)((R.n_rays + 127) / 128);
+        if (argc > 3 && !strcmp(argv[3], "v17")) {
+            R.run("product-like, checked loop only (reference)", [&] { k_product_like<<<b3, 128>>>(a, q); }, true);
+            R.run("interior poses skip the bounds tests", [&] { k_product_like_t<true><<<b3, 128>>>(a, q); });
+            R.run("checked loop only (templated twin)", [&] { k_product_like_t<false><<<b3, 128>>>(a, q); });
+            CK(cudaFuncSetAttribute(k_product_like_t<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
+            CK(cudaFuncSetAttribute(k_product_like_t<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
+            R.run("interior + carveout max L1", [&] { k_product_like_t<true><<<b3, 128>>>(a, q); });
+            R.run("checked + carveout max L1", [&] { k_product_like_t<false><<<b3, 128>>>(a, q); });
+            R.run("product-like again", [&] { k_product_like<<<b3, 128>>>(a, q); });
+            return 0;
+        }
+        if (argc > 3 && !strcmp(argv[3], "v18")) {
+            R.run("product-like (reference of this table)", [&] { k_product_like<<<b3, 128>>>(a, q); }, true);
+            auto mlp = [&](auto rtag) {
+                constexpr int RR = decltype(rtag)::value;
+                const unsigned cpp = (unsigned)((a.num_beams + 32 * RR - 1) / (32 * RR));
+                int sf = 1; while ((1u << sf) < cpp) ++sf;
+                const unsigned long long mg = ((1ull << (31 + sf)) + cpp - 1) / cpp;
+                const unsigned long long warps = (unsigned long long)a.num_poses * cpp;
+                k_mlp<RR><<<(unsigned)((warps + 3) / 4), 128>>>(a, q, cpp, (unsigned)mg, (unsigned)(sf - 1));
+            };
+            R.run("mlp R=1 (pose-aligned warps, control)", [&] { mlp(std::integral_constant<int, 1>{}); });
+            R.run("mlp R=2", [&] { mlp(std::integral_constant<int, 2>{}); });
+            R.run("mlp R=3", [&] { mlp(std::integral_constant<int, 3>{}); });
+            R.run("mlp R=4", [&] { mlp(std::integral_constant<int, 4>{}); });
+            R.run("product-like again", [&] { k_product_like<<<b3, 128>>>(a, q); });
+            return 0;
+        }
+        if (argc > 3 && !strcmp(argv[3], "diag2")) {
+            Diag2 D;
+            const size_t nwarps = (R.n_rays + 31) / 32;
+            CK(cudaMalloc(&D.t_first, nwarps * 8)); CK(cudaMalloc(&D.t_last, nwarps * 8)); CK(cudaMalloc(&D.max_steps, nwarps * 4));
+            CK(cudaMalloc(&D.ray_steps, R.n_rays * 4)); CK(cudaMalloc(&D.ray_cycles, R.n_rays * 4));
+            for (int rep = 0; rep < 3; ++rep) {
+                CK(cudaMemset(D.t_last, 0, nwarps * 8)); CK(cudaMemset(D.max_steps, 0, nwarps * 4));
+                CK(cudaMemsetAsync(R.flush, rep, 256u << 20));
+                k_diag2<<<b3, 128>>>(a, q, D);
+                CK(cudaDeviceSynchronize());
+            }
+            std::vector<unsigned long long> tf(nwarps), tl(nwarps);
+            std::vector<unsigned> ms(nwarps), rs(R.n_rays), rc(R.n_rays);
+            CK(cudaMemcpy(tf.data(), D.t_first, nwarps * 8, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(tl.data(), D.t_last, nwarps * 8, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(ms.data(), D.max_steps, nwarps * 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(rs.data(), D.ray_steps, R.n_rays * 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(rc.data(), D.ray_cycles, R.n_rays * 4, cudaMemcpyDeviceToHost));
+            unsigned long long t0 = ~0ull, tmax = 0;
+            for (auto v : tf) t0 = v < t0 ? v : t0;
+            for (auto v : tl) tmax = v > tmax ? v : tmax;
+            printf("DIAG2 kernel span %.1f us\n", (tmax - t0) / 1e3);
+            for (unsigned long long tick = 0; tick <= (tmax - t0); tick += 4000) {
+                size_t running = 0, started = 0;
+                for (size_t w = 0; w < nwarps; ++w) { if (tf[w] - t0 <= tick) { ++started; if (tl[w] - t0 > tick) ++running; } }
+                printf("DIAG2 t=%5.1f us  warps started %7zu  running %6zu\n", tick / 1e3, started, running);
+            }
+            // the 25 warps that finish last
+            std::vector<size_t> idx(nwarps);
+            for (size_t w = 0; w < nwarps; ++w) idx[w] = w;
+            std::partial_sort(idx.begin(), idx.begin() + 25, idx.end(), [&](size_t x, size_t y) { return tl[x] > tl[y]; });
+            for (int n = 0; n < 25; ++n) {
+                const size_t w = idx[n];
+                printf("DIAG2 last #%2d: warp %7zu start %6.1f us end %6.1f us  lived %5.1f us  max steps %u\n", n, w,
+                       (tf[w] - t0) / 1e3, (tl[w] - t0) / 1e3, (tl[w] - tf[w]) / 1e3, ms[w]);
+            }
+            for (int mode = 0; mode < 2; ++mode) {
+                for (int rep = 0; rep < 3; ++rep) {
+                    CK(cudaMemsetAsync(R.flush, rep, 256u << 20));
+                    if (mode == 0) k_diag3<0><<<b3, 128>>>(a, q, D.t_first, D.t_last); else k_diag3<1><<<b3, 128>>>(a, q, D.t_first, D.t_last);
+                    CK(cudaDeviceSynchronize());
+                }
+                CK(cudaMemcpy(tf.data(), D.t_first, nwarps * 8, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(tl.data(), D.t_last, nwarps * 8, cudaMemcpyDeviceToHost));
+                t0 = ~0ull; tmax = 0;
+                for (auto v : tf) t0 = v < t0 ? v : t0;
+                for (auto v : tl) tmax = v > tmax ? v : tmax;
+                printf("DIAG3 mode %d (0 = product march, 1 = predicted-sample touch) kernel span %.1f us\n", mode, (tmax - t0) / 1e3);
+                for (unsigned long long tick = 0; tick <= (tmax - t0); tick += 2000) {
+                    size_t running = 0, started = 0;
+                    for (size_t w = 0; w < nwarps; ++w) { if (tf[w] - t0 <= tick) { ++started; if (tl[w] - t0 > tick) ++running; } }
+                    if (tick % 8000 == 0 || started == nwarps) printf("DIAG3 t=%5.1f us  warps started %7zu  running %6zu\n", tick / 1e3, started, running);
+                }
+                for (size_t w = 0; w < nwarps; ++w) idx[w] = w;
+                std::partial_sort(idx.begin(), idx.begin() + 25, idx.end(), [&](size_t x, size_t y) { return tl[x] > tl[y]; });
+                for (int n = 0; n < 25; ++n) {
+                    const size_t w = idx[n];
+                    printf("DIAG3 last #%2d: warp %7zu start %6.1f us end %6.1f us  lived %5.1f us  max steps %u  (%.0f cycles/step)\n", n, w,
+                           (tf[w] - t0) / 1e3, (tl[w] - t0) / 1e3, (tl[w] - tf[w]) / 1e3, ms[w], (tl[w] - tf[w]) * 1.965 / ms[w]);
+                }
+                for (int b = 0; b < 9; ++b) {
+                    const unsigned edges2[10] = {1, 4, 8, 16, 32, 48, 64, 96, 128, 100000};
+                    double life = 0; size_t n = 0;
+                    for (size_t w = 0; w < nwarps; ++w) if (ms[w] >= edges2[b] && ms[w] < edges2[b + 1]) { life += (double)(tl[w] - tf[w]); ++n; }
+                    if (n) printf("DIAG3 warps with max steps %u..%u: %zu warps, mean lifetime %.2f us\n", edges2[b], edges2[b + 1] - 1, n, life / n / 1e3);
+                }
+            }
+            // cycles per step by ray length
+            const unsigned edges[10] = {1, 4, 8, 16, 32, 48, 64, 96, 128, 100000};
+            for (int b = 0; b < 9; ++b) {
+                double cyc = 0, stp = 0; size_t n = 0;
+                for (size_t i = 0; i < R.n_rays; ++i) if (rs[i] >= edges[b] && rs[i] < edges[b + 1]) { cyc += rc[i]; stp += rs[i]; ++n; }
+                if (n) printf("DIAG2 rays with %u..%u steps: %zu rays, %.0f cycles/ray, %.0f cycles/step\n", edges[b], edges[b + 1] - 1, n, cyc / n, cyc / stp);
+            }
+            // warp lifetime by max steps
+            for (int b = 0; b < 9; ++b) {
+                double life = 0; size_t n = 0;
+                for (size_t w = 0; w < nwarps; ++w) if (ms[w] >= edges[b] && ms[w] < edges[b + 1]) { life += (double)(tl[w] - tf[w]); ++n; }
+                if (n) printf("DIAG2 warps with max steps %u..%u: %zu warps, mean lifetime %.2f us\n", edges[b], edges[b + 1] - 1, n, life / n / 1e3);
+            }
+            return 0;
+        }
+        if (argc > 3 && !strcmp(argv[3], "v19")) {
+            R.run("product-like (reference of this table)", [&] { k_product_like<<<b3, 128>>>(a, q); }, true);
+#define V19(AFTER, K) R.run("touch the predicted sample: after" #AFTER " K" #K, [&] { k_v19<AFTER, K><<<b3, 128>>>(a, q); });
+            V19(32, 2) V19(32, 3) V19(32, 4) V19(32, 5) V19(32, 6) V19(32, 8) V19(32, 12)
+            V19(24, 3) V19(24, 4) V19(24, 6) V19(16, 3) V19(16, 4) V19(16, 6) V19(12, 4) V19(8, 4) V19(48, 4)
+            R.run("product-like again", [&] { k_product_like<<<b3, 128>>>(a, q); });
+            return 0;
+        }
+        if (argc > 3 && !strcmp(argv[3], "chain")) {
+            const int n = 2049;
+            float *cf; unsigned *osteps; long long *ocyc; float *sink;
+            CK(cudaMalloc(&cf, (size_t)n * n * 4)); CK(cudaMalloc(&osteps, 128)); CK(cudaMalloc(&ocyc, 256)); CK(cudaMalloc(&sink, 128));
+            MarchParams CP = a.P; CP.dist = cf; CP.rows = n; CP.cols = n; CP.frows = (float)n; CP.fcols = (float)n; CP.max_range = 300.f;
+            for (float dval : {1.0f, 2.0f, 3.0f, 5.0f}) {
+                std::vector<float> h((size_t)n * n, dval);
+                CK(cudaMemcpy(cf, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+                const unsigned nsteps = 1 + (unsigned)(300.0f / fmaxf(dval * 0.999f, 1.0f));
+                for (int dir = 0; dir < 3; ++dir) {
+                    const float th0 = dir == 0 ? 0.02f : dir == 1 ? 1.55f : 0.8f;   // dx ~ 1: across rows; dy ~ 1: along a row; diagonal
+                    for (int lanes : {1, 4, 32}) {
+                        for (int mode = 0; mode < 3; ++mode) {
+                            long long cyc[32]; unsigned stp[32];
+                            for (int rep = 0; rep < 2; ++rep) {   // second repetition: L2 warm (L1 is invalidated per launch)
+                                if (mode == 0) k_chain<0><<<1, 32>>>(CP, 1000.5f, 1000.5f, th0, lanes, osteps, ocyc, sink);
+                                else if (mode == 1) k_chain<1><<<1, 32>>>(CP, 1000.5f, 1000.5f, th0, lanes, osteps, ocyc, sink);
+                                else k_chain<2><<<1, 32>>>(CP, 1000.5f, 1000.5f, th0, lanes, osteps, ocyc, sink);
+                                CK(cudaDeviceSynchronize());
+                            }
+                            CK(cudaMemcpy(cyc, ocyc, 256, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(stp, osteps, 128, cudaMemcpyDeviceToHost));
+                            printf("CHAIN d=%.0f dir=%s lanes=%2d mode=%d (%s): %5.1f cycles/step (%u steps)\n", dval,
+                                   dir == 0 ? "across-rows" : dir == 1 ? "along-row " : "diagonal   ", lanes, mode,
+                                   mode == 0 ? "plain loop   " : mode == 1 ? "product march" : "predicted K6 ", (double)cyc[0] / nsteps, nsteps);
+                        }
+                    }
+                }
+            }
+            return 0;
+        }
+        if (argc > 3 && !strcmp(argv[3], "step")) {
+            const int n = 64;
+            float *cf; unsigned *osteps; long long *ocyc; float *sink;
+            CK(cudaMalloc(&cf, (size_t)n * n * 4)); CK(cudaMalloc(&osteps, 128)); CK(cudaMalloc(&ocyc, 256)); CK(cudaMalloc(&sink, 128));
+            MarchParams CP = a.P; CP.dist = cf; CP.rows = n; CP.cols = n; CP.frows = (float)n; CP.fcols = (float)n; CP.max_range = 50.f;
+            std::vector<float> h((size_t)n * n, 1.0f);
+            CK(cudaMemcpy(cf, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+            for (int dir = 0; dir < 2; ++dir) {
+                const float th0 = dir == 0 ? 0.02f : 0.8f;
+                for (int var = 0; var < 4; ++var) {
+                    long long cyc; unsigned stp;
+                    for (int rep = 0; rep < 2; ++rep) {
+                        if (var == 0) k_step<0><<<1, 1>>>(CP, 5.5f, 5.5f, th0, 8, ocyc, osteps, sink);
+                        else if (var == 1) k_step<1><<<1, 1>>>(CP, 5.5f, 5.5f, th0, 8, ocyc, osteps, sink);
+                        else if (var == 2) k_step<2><<<1, 1>>>(CP, 5.5f, 5.5f, th0, 8, ocyc, osteps, sink);
+                        else k_step<3><<<1, 1>>>(CP, 5.5f, 5.5f, th0, 8, ocyc, osteps, sink);
+                        CK(cudaDeviceSynchronize());
+                    }
+                    CK(cudaMemcpy(&cyc, ocyc, 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&stp, osteps, 4, cudaMemcpyDeviceToHost));
+                    printf("STEP dir=%d var=%d: %6.1f cycles/step (%u steps, all L1 hits)\n", dir, var, (double)cyc / stp, stp);
+                }
+            }
+            return 0;
+        }
+        if (argc > 3 && !strcmp(argv[3], "v16")) {
+            const unsigned ngroups = (unsigned)((R.n_rays + 31) / 32);
+            R.run("product-like (reference of this table)", [&] { k_product_like<<<b3, 128>>>(a, q); }, true);
+            R.run("v16 plain (restructured, no new idea)", [&] { k_v16<false, 0><<<b3, 128>>>(a, q); });
+            R.run("v16 safe", [&] { k_v16<true, 0><<<b3, 128>>>(a, q); });
+            R.run("v16 coop after32", [&] { k_v16<false, 32><<<b3, 128>>>(a, q); });
+            R.run("v16 coop after24", [&] { k_v16<false, 24><<<b3, 128>>>(a, q); });
+            R.run("v16 coop after16", [&] { k_v16<false, 16><<<b3, 128>>>(a, q); });
+            R.run("v16 coop after12", [&] { k_v16<false, 12><<<b3, 128>>>(a, q); });
+            R.run("v16 safe + coop after24", [&] { k_v16<true, 24><<<b3, 128>>>(a, q); });
+            R.run("v16 safe + coop after16", [&] { k_v16<true, 16><<<b3, 128>>>(a, q); });
+#define V16P(SAFE, COOP, CH, PCT) { char nm[96]; snprintf(nm, sizeof nm, "v16 persistent safe%d coop%d chunk%d for %d%%", SAFE, COOP, CH, PCT); \
+            const unsigned cg = (unsigned)((unsigned long long)ngroups * PCT / 100) / CH * CH; \
+            R.run(nm, [&] { k_v16p<SAFE, COOP, CH><<<sms * 16, 128>>>(a, q, ngroups, cg); }); }
+            V16P(false, 0, 4, 90) V16P(false, 0, 4, 97) V16P(false, 0, 2, 95) V16P(false, 0, 8, 90) V16P(false, 0, 1, 0)
+            V16P(true, 0, 4, 90) V16P(true, 24, 4, 90) V16P(true, 24, 4, 97) V16P(true, 16, 2, 95)
+            R.run("product-like again", [&] { k_product_like<<<b3, 128>>>(a, q); });
+            return 0;
+        }
         R.run("ray3 opt0", [&] { k_ray3<0><<<b3, 128>>>(a, q); });
         R.run("ray3 opt1 magic", [&] { k_ray3<1><<<b3, 128>>>(a, q); });
         R.run("ray3 opt2 hit-after", [&] { k_ray3<2><<<b3, 128>>>(a, q); });
