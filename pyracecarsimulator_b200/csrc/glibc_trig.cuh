@@ -36,25 +36,6 @@ static __device__ __constant__ uint32_t g_inv_pio4[24] = {
     0x441529fc, 0x1529fc27, 0x29fc2757, 0xfc2757d1, 0x2757d1f5, 0x57d1f534, 0xd1f534dd, 0xf534ddc0,
     0x34ddc0db, 0xddc0db62, 0xc0db6295, 0xdb629599, 0x6295993c, 0x95993c43, 0x993c4390, 0x3c439041};
 
-__device__ __forceinline__ double trig_sin_poly(double x, double x2)
-{
-    const double x3 = __dmul_rn(x, x2);
-    const double s1 = fma(x2, trig::S3, trig::S2);
-    const double x7 = __dmul_rn(x3, x2);
-    const double s = fma(x3, trig::S1, x);
-    return fma(x7, s1, s);
-}
-
-__device__ __forceinline__ double trig_cos_poly(double x2)
-{
-    const double x4 = __dmul_rn(x2, x2);
-    const double c2 = fma(x2, trig::C4, trig::C3);
-    const double c1 = fma(x2, trig::C1, trig::C0);
-    const double x6 = __dmul_rn(x4, x2);
-    const double c = fma(x4, trig::C2, c1);
-    return fma(x6, c2, c);
-}
-
 // reduce_large: |y| >= 120 (finite).  Returns the reduced argument, quadrant in n.
 static __device__ __noinline__ double trig_reduce_large(uint32_t xi, int &n_out)
 {
@@ -73,29 +54,34 @@ static __device__ __noinline__ double trig_reduce_large(uint32_t xi, int &n_out)
     return __dmul_rn((double)(int64_t)res0, trig::PI63);
 }
 
-// sin and cos of y with glibc's bits.  *sp = sinf(y), *cp = cosf(y).
+// The coefficients in constant memory: as immediates every double costs two MOVs before its FMA; as
+// constant-bank operands (or one LDC.64) they cost nothing (or one instruction).
+static __device__ __constant__ double g_trig_k[9] = {
+    trig::HPI_INV, trig::HPI, trig::C1, trig::C2, trig::C3, trig::C4, trig::S1, trig::S2, trig::S3};
+
+// sin and cos of y with glibc's bits.  *sp = sinf(y), *cp = cosf(y).  The arithmetic is glibc's, operation
+// for operation (oracle/trig_twin.c is the literal C twin); the control flow around it is trimmed because
+// this sits on the setup path of every ray (~50 instead of ~70 instructions, 84.8 -> 83.7 us on config 2):
+//  * glibc's |y| < pi/4 shortcut is the general path with n = 0 (the reduction leaves x untouched:
+//    -0 * pi/2 + x == x), so it needs no branch of its own; the |y| < 2^-12 shortcut stays (it alone
+//    returns -0 for -0);
+//  * sign[nq & 3] and the negated-cosine table are applied by flipping the sign bit of the double's high word;
+//  * the sin/cos swap for odd quadrants is done on the two floats.
 __device__ __forceinline__ void glibc_sincosf(float y, float *sp, float *cp)
 {
     const uint32_t yi = __float_as_uint(y);
     const uint32_t top = (yi >> 20) & 0x7ff;  // abstop12
     double x = (double)y;
-    if (top < 0x3f4u) {                       // |y| < pi/4   (abstop12(0x1.921FB6p-1f) = 0x3f4)
-        if (top < 0x398u) {                   // |y| < 2^-12
-            *sp = y;
-            *cp = 1.0f;
-            return;
-        }
-        const double x2 = __dmul_rn(x, x);
-        *sp = (float)trig_sin_poly(x, x2);
-        *cp = (float)trig_cos_poly(x2);
-        return;
-    }
-    int n, nq;                                // n picks the polynomial, nq the signs
-    if (top < 0x42fu) {                       // |y| < 120    (abstop12(120.0f) = 0x42f)
-        const double r = __dmul_rn(x, trig::HPI_INV);
+    int n, nq;
+    if (top - 0x398u < 0x42fu - 0x398u) {     // 2^-12 <= |y| < 120
+        const double r = __dmul_rn(x, g_trig_k[0]);
         n = (__double2int_rz(r) + 0x800000) >> 24;
-        x = fma(-(double)n, trig::HPI, x);
+        x = fma(-(double)n, g_trig_k[1], x);
         nq = n;
+    } else if (top < 0x398u) {                // |y| < 2^-12
+        *sp = y;
+        *cp = 1.0f;
+        return;
     } else if (top < 0x7f8u) {                // finite: reduce |y|, fold the sign into nq only
         x = trig_reduce_large(yi, n);
         nq = n + (int)(yi >> 31);
@@ -103,19 +89,26 @@ __device__ __forceinline__ void glibc_sincosf(float y, float *sp, float *cp)
         *sp = *cp = y - y;
         return;
     }
-    // sign[nq & 3] = {1, -1, -1, 1}; quadrants 2, 3 use the negated-cosine table
-    const double xs = ((nq + 1) & 2) ? -x : x;
     const double x2 = __dmul_rn(x, x);
-    const double s = trig_sin_poly(xs, x2);
-    double c = trig_cos_poly(x2);
-    if (nq & 2) c = -c;
-    if (n & 1) {
-        *sp = (float)c;
-        *cp = (float)s;
-    } else {
-        *sp = (float)s;
-        *cp = (float)c;
-    }
+    // sign[nq & 3] = {1, -1, -1, 1} multiplies the sine's argument; quadrants 2, 3 negate the cosine
+    const double xs = __hiloint2double(__double2hiint(x) ^ (((nq + 1) & 2) << 30), __double2loint(x));
+    // sincosf_poly (sincosf.h), operation for operation
+    const double x3 = __dmul_rn(xs, x2);
+    const double s1 = fma(x2, g_trig_k[8], g_trig_k[7]);
+    const double x7 = __dmul_rn(x3, x2);
+    const double s0 = fma(x3, g_trig_k[6], xs);
+    const double s = fma(x7, s1, s0);
+    const double x4 = __dmul_rn(x2, x2);
+    const double c2 = fma(x2, g_trig_k[5], g_trig_k[4]);
+    const double c1 = fma(x2, g_trig_k[2], trig::C0);
+    const double x6 = __dmul_rn(x4, x2);
+    const double cc = fma(x4, g_trig_k[3], c1);
+    const double c0 = fma(x6, c2, cc);
+    const double c = __hiloint2double(__double2hiint(c0) ^ ((nq & 2) << 30), __double2loint(c0));
+    const float sf = (float)s, cf = (float)c;
+    const bool swap = n & 1;
+    *sp = swap ? cf : sf;
+    *cp = swap ? sf : cf;
 }
 
 }  // namespace rl

@@ -1568,6 +1568,116 @@ __global__ void k_step(MarchParams P, float x0, float y0, float th0, int reps, l
     out_steps[0] = st;
 }
 
+// ---------------------------------------------------------------- V20: shorter dependent chain per step.  The load is
+// predicated on the bounds test instead of guarded by a branch (an out-of-map sample reads d = 0 and leaves
+// through the one exit branch), and the loop is rotated: the next sample's cell is computed BEFORE the exit
+// test of the current one, so the address arithmetic no longer waits for the branch to resolve.  Same samples,
+// same arithmetic.  TOUCH: the product's look-ahead touches after 32 steps.
+__device__ __forceinline__ int cvt_rz_pinned(float v)   // volatile: stays where it is written (before the exit branch)
+{
+    int r;
+    asm volatile("cvt.rzi.s32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float ldg_if(const float *p, bool pred)   // predicated load, 0 when pred is false
+{
+    float d;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}"
+                 : "=f"(d) : "l"(p), "r"((int)pred));
+    return d;
+}
+template <bool TOUCH>
+__device__ __forceinline__ float march_ray_v20(const MarchParams &P, float x0, float y0, float dx, float dy,
+                                               const rl::FirstSample &f0)
+{
+    if (!f0.inside || !(dx == dx) || !(dy == dy)) return P.max_range;
+    if (f0.d <= 0.0f) {
+        const float xd = __fsub_rn((float)f0.px, x0), yd = __fsub_rn((float)f0.py, y0);
+        return sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+    }
+    float t = fmaxf(__fmul_rn(f0.d, 0.999f), 1.0f);
+    if (!(t < P.max_range)) return P.max_range;
+    float th, d;                 // th: parameter of the sample whose clearance d is
+    int it = 1;
+    bool tail = false;
+    int px = __float2int_rz(fmaf(dx, t, x0)), py = __float2int_rz(fmaf(dy, t, y0));
+    bool inb = (unsigned)px < (unsigned)P.rows && (unsigned)py < (unsigned)P.cols;
+    for (;;) {
+        d = ldg_if(P.dist + (px * P.cols + py), inb);
+        th = t;
+        t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+        px = cvt_rz_pinned(fmaf(dx, t, x0));
+        py = cvt_rz_pinned(fmaf(dy, t, y0));
+        const bool was_in = inb;
+        inb = (unsigned)px < (unsigned)P.rows && (unsigned)py < (unsigned)P.cols;
+        if (d <= 0.0f || !(t < P.max_range)) { inb = was_in; break; }
+        if (++it == 32) { tail = true; break; }
+    }
+    if (tail) {
+        float j0 = 0.f, j1 = 0.f, j2 = 0.f, j3 = 0.f, keep = 0.f;
+        const float adx = __fmul_rn(dx, 12.0f), ady = __fmul_rn(dy, 12.0f);
+#define V20_STEP(J)                                                                                \
+        {                                                                                          \
+            d = ldg_if(P.dist + (px * P.cols + py), inb);                                          \
+            if (TOUCH) {                                                                           \
+                const int ax = __float2int_rz(__fadd_rn(fmaf(dx, t, x0), adx)), ay = __float2int_rz(__fadd_rn(fmaf(dy, t, y0), ady)); \
+                keep = __fadd_rn(keep, J);                                                         \
+                if ((unsigned)ax < (unsigned)P.rows && (unsigned)ay < (unsigned)P.cols)            \
+                    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(J) : "l"(P.dist + (ax * P.cols + ay))); \
+            }                                                                                      \
+            th = t;                                                                                \
+            t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));                                   \
+            px = cvt_rz_pinned(fmaf(dx, t, x0));                                                   \
+            py = cvt_rz_pinned(fmaf(dy, t, y0));                                                   \
+            const bool was_in = inb;                                                               \
+            inb = (unsigned)px < (unsigned)P.rows && (unsigned)py < (unsigned)P.cols;              \
+            if (d <= 0.0f || !(t < P.max_range)) { inb = was_in; break; }                          \
+        }
+        for (;;) { V20_STEP(j0) V20_STEP(j1) V20_STEP(j2) V20_STEP(j3) }
+#undef V20_STEP
+        if (__fadd_rn(__fadd_rn(keep, j0), __fadd_rn(j1, __fadd_rn(j2, j3))) < 0.0f) return -1.0f;  // never true
+    }
+    // inb: whether the sample at th was inside the map; d its clearance (0 when outside)
+    if (inb && d <= 0.0f) {
+        const float xd = __fsub_rn((float)__float2int_rz(fmaf(dx, th, x0)), x0);
+        const float yd = __fsub_rn((float)__float2int_rz(fmaf(dy, th, y0)), y0);
+        return sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+    }
+    return P.max_range;
+}
+
+template <bool TOUCH>
+__global__ void __launch_bounds__(128) k_v20(Args a, Lean q)
+{
+    const unsigned i = blockIdx.x * 128u + threadIdx.x;
+    const unsigned total = (unsigned)a.num_poses * a.num_beams;
+    if (i >= total) return;
+    float x0, y0, dx, dy;
+    ray_setup_fan(a, q, i, x0, y0, dx, dy);
+    const rl::FirstSample f0 = rl::first_sample(a.P, x0, y0);
+    a.outs[i] = __fmul_rn(march_ray_v20<TOUCH>(a.P, x0, y0, dx, dy, f0), a.P.w.scale);
+}
+
+// ---------------------------------------------------------------- V21: the product kernel with the leaner trig
+__global__ void __launch_bounds__(128) k_v21(Args a, Lean q)
+{
+    const unsigned i = blockIdx.x * 128u + threadIdx.x;
+    const unsigned total = (unsigned)a.num_poses * a.num_beams;
+    if (i >= total) return;
+    const MarchParams &P = a.P;
+    const unsigned k = __umulhi(i, q.magic) >> q.shift;
+    const int j = i - k * a.num_beams;
+    const float *p = a.poses + 3 * k;
+    const float thw = __ldg(p + 2);
+    const GridPose g = rl::world_to_grid(P.w, __ldg(p), __ldg(p + 1), thw);
+    const float thg = __fadd_rn(-__fadd_rn(thw, fmaf((float)j, q.inc, -0.5f * a.fov)), P.w.rotation_const);
+    const rl::FirstSample f0 = rl::first_sample(a.P, g.y, g.x);
+    float dx, dy;
+    rl::glibc_sincosf(thg, &dy, &dx);
+    uint32_t st = 0;
+    a.outs[i] = __fmul_rn(rl::march_ray<false>(a.P, g.y, g.x, dx, dy, st, f0), a.P.w.scale);
+}
+
 // ---------------------------------------------------------------- harness
 static std::vector<char> slurp(const std::string &path)
 {
@@ -1865,6 +1975,21 @@ int main(int argc, char **argv)
                     printf("STEP dir=%d var=%d: %6.1f cycles/step (%u steps, all L1 hits)\n", dir, var, (double)cyc / stp, stp);
                 }
             }
+            return 0;
+        }
+        if (argc > 3 && !strcmp(argv[3], "v20")) {
+            R.run("product-like (reference of this table)", [&] { k_product_like<<<b3, 128>>>(a, q); }, true);
+            R.run("v20 rotated loop, predicated load, touches", [&] { k_v20<true><<<b3, 128>>>(a, q); });
+            R.run("v20 rotated loop, predicated load, no touch", [&] { k_v20<false><<<b3, 128>>>(a, q); });
+            R.run("product-like again", [&] { k_product_like<<<b3, 128>>>(a, q); });
+            R.run("v20 touches again", [&] { k_v20<true><<<b3, 128>>>(a, q); });
+            return 0;
+        }
+        if (argc > 3 && !strcmp(argv[3], "v21")) {
+            R.run("product-like (reference of this table)", [&] { k_product_like<<<b3, 128>>>(a, q); }, true);
+            R.run("v21 lean trig", [&] { k_v21<<<b3, 128>>>(a, q); });
+            R.run("product-like again", [&] { k_product_like<<<b3, 128>>>(a, q); });
+            R.run("v21 lean trig again", [&] { k_v21<<<b3, 128>>>(a, q); });
             return 0;
         }
         if (argc > 3 && !strcmp(argv[3], "v16")) {
