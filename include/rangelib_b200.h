@@ -204,6 +204,18 @@ RL_API int32_t rl_rollout(rl_marcher *m, rl_car *car, double *d_states, const do
                           int32_t *d_crash_index, double *d_reward, float *d_poses, double *d_vsum,
                           void *stream);
 
+/* The action schedule MCTS.rollout draws on the host (scripts/mcts.py:216-222: every 10th step      */
+/* rand_steer = uniform(-max_steer_ang, max_steer_ang), then rand_speed = uniform(0, max_speed)),    */
+/* generated on the device instead so that no host tensor feeds rl_rollout: d_actions (n_cars,       */
+/* n_actions, 2) fp64 = (speed, steer).  Counter-based (Philox4x32-10): block (action, car_lo,        */
+/* car_hi, stream_id) under key (seed_lo, seed_hi); words 0,1 -> steer, words 2,3 -> speed, each the  */
+/* 53-bit double ((a>>5)*2^26 + (b>>6))/2^53 mapped as lo + (hi-lo)*u.  Reproducible for any launch   */
+/* shape and GPU count (a rank generates its own car range by passing global car indices through     */
+/* car_offset).                                                                                       */
+RL_API int32_t rl_rollout_actions(double *d_actions, int64_t n_cars, int32_t n_actions, uint64_t seed,
+                                  uint32_t stream_id, int64_t car_offset, double speed_lo, double speed_hi,
+                                  double steer_lo, double steer_hi, int32_t device, void *stream);
+
 /* FollowGap(ws, max_distance, max_angle, angle_inc).eval(scan, num_rays) for `num_scans` scans at */
 /* once (followgap/followgap.hpp:104-129; caller scripts/mcts.py:262-267): d_scans is             */
 /* (num_scans, num_rays) fp32 ranges in metres, d_out[s] the steering angle.  num_rays >= 10.      */

@@ -24,12 +24,14 @@ f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 i8p = np.ctypeslib.ndpointer(np.int8, flags="C_CONTIGUOUS")
 i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
 
 
 def build(force=False):
     """Compile liboracle.so (and _ref/ when /root/reference is present)."""
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("rangelib_oracle.c", "car_oracle.c", "trig_twin.c", "followgap_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("rangelib_oracle.c", "car_oracle.c", "trig_twin.c", "followgap_oracle.c",
+                                             "philox_oracle.c")]
     stale = force or not os.path.exists(so) or any(
         os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     ref_so = os.path.join(_HERE, "_ref", "libracecar_ref.so")
@@ -94,6 +96,9 @@ def lib():
     L.orc_car_scan_pose.argtypes = [f64p, C.c_double, f64p]
     L.orc_car_edge_distances.argtypes = [C.POINTER(CarParams), C.c_int, C.c_double, C.c_double,
                                          C.c_double, f64p]
+    L.orc_philox4x32_10.argtypes = [u32p, u32p, u32p]
+    L.orc_rollout_actions.argtypes = [f64p, C.c_int64, C.c_int32, C.c_uint64, C.c_uint32, C.c_int64,
+                                      C.c_double, C.c_double, C.c_double, C.c_double]
     L.orc_car_is_crashed.restype = C.c_int
     L.orc_car_is_crashed.argtypes = [f32p, f64p, C.c_int, C.c_int, C.c_double]
     _LIB = L
@@ -244,6 +249,24 @@ def car_edge_distances(params, num_rays, min_ang, inc, scan_dist_to_base):
 def car_is_crashed(rays, edge, num_rays, poses, crash_thresh):
     rays = np.ascontiguousarray(rays, dtype=np.float32)
     return int(lib().orc_car_is_crashed(rays, edge, num_rays, poses, crash_thresh))
+
+
+def philox4x32_10(ctr, key):
+    """One Philox4x32-10 block: 4 counter words, 2 key words -> 4 output words (uint32)."""
+    ctr = np.ascontiguousarray(ctr, dtype=np.uint32)
+    key = np.ascontiguousarray(key, dtype=np.uint32)
+    out = np.empty(4, dtype=np.uint32)
+    lib().orc_philox4x32_10(ctr, key, out)
+    return out
+
+
+def rollout_actions(n_cars, n_actions, seed=42, stream_id=0, car_offset=0, speed_range=(0.0, 7.0),
+                    steer_range=(-0.4189, 0.4189)):
+    """(n_cars, n_actions, 2) float64 (speed, steer): the schedule rl_rollout_actions draws on the device."""
+    out = np.empty((n_cars, n_actions, 2), dtype=np.float64)
+    lib().orc_rollout_actions(out.reshape(-1), n_cars, n_actions, seed, stream_id, car_offset,
+                              speed_range[0], speed_range[1], steer_range[0], steer_range[1])
+    return out
 
 
 def followgap_eval(lidar, max_distance=15.0, max_angle=0.4189, angle_inc=0.004):

@@ -151,6 +151,49 @@ car_step_kernel(CarParams p, double *__restrict__ states, const double *__restri
     store_state(states + 11 * c, s);
 }
 
+// Rollout action schedule generated on the device: MCTS.rollout draws
+// rand_steer = uniform(-max_steer_ang, max_steer_ang) and then rand_speed = uniform(0, max_speed) on
+// every action_every-th step (scripts/mcts.py:216-222).  Here every (car, action) pair owns one
+// Philox4x32-10 block -- counter (action, car_lo, car_hi, stream_id), key (seed_lo, seed_hi) -- so the
+// schedule is reproducible whatever the launch shape and identical to oracle/philox_oracle.c: words
+// 0,1 make the steer variate, words 2,3 the speed variate, each as the 53-bit double
+// ((a >> 5) * 2^26 + (b >> 6)) / 2^53 scaled the way numpy's uniform() does, lo + (hi - lo) * u.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ double unit_double(uint32_t a, uint32_t b)
+{
+    return __dmul_rn(__dadd_rn(__dmul_rn((double)(a >> 5), 67108864.0), (double)(b >> 6)), 1.0 / 9007199254740992.0);
+}
+
+__global__ void __launch_bounds__(256)
+rollout_actions_kernel(double *__restrict__ actions, int64_t n_cars, int n_actions, uint64_t seed,
+                       uint32_t stream_id, int64_t car_offset, double speed_lo, double speed_hi, double steer_lo, double steer_hi)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cars * n_actions) return;
+    const int64_t c = i / n_actions;
+    const uint32_t a = (uint32_t)(i - c * n_actions);
+    const uint64_t gc = (uint64_t)(c + car_offset);   // global car index
+    uint32_t w[4];
+    philox4x32_10(a, (uint32_t)(gc & 0xffffffffu), (uint32_t)(gc >> 32), stream_id,
+                  (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), w);
+    const double steer = __dadd_rn(steer_lo, __dmul_rn(__dsub_rn(steer_hi, steer_lo), unit_double(w[0], w[1])));
+    const double speed = __dadd_rn(speed_lo, __dmul_rn(__dsub_rn(speed_hi, speed_lo), unit_double(w[2], w[3])));
+    actions[2 * i] = speed;
+    actions[2 * i + 1] = steer;
+}
+
 __global__ void fill_i32_kernel(int32_t *p, int64_t n, int32_t v)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -378,6 +421,25 @@ RL_API int32_t rl_scan_crash(rl_marcher *m, rl_car *car, const float *d_poses, i
         march_crash_kernel<false, false><<<blocks_for(total, 256), 256, 0, s>>>(
             P, d_poses, car->d_edge, total, car->num_rays, poses_per_group, groups, fov, fov / (float)car->num_rays, car->p.crash_thresh, d_first, nullptr);
     finalize_first_kernel<<<blocks_for(groups, 256), 256, 0, s>>>(d_first, groups, poses_per_group, nullptr, nullptr);
+    RL_CUDA(cudaGetLastError());
+    return RL_OK;
+}
+
+// The action schedule of MCTS.rollout (scripts/mcts.py:216-222) for n_cars cars, drawn on the device:
+// d_actions (n_cars, n_actions, 2) fp64 = (speed in [speed_lo, speed_hi), steer in [steer_lo, steer_hi)).
+RL_API int32_t rl_rollout_actions(double *d_actions, int64_t n_cars, int32_t n_actions, uint64_t seed,
+                                  uint32_t stream_id, int64_t car_offset, double speed_lo, double speed_hi,
+                                  double steer_lo, double steer_hi, int32_t device, void *stream)
+{
+    if (n_cars < 0 || n_actions <= 0 || car_offset < 0 || (n_cars > 0 && !d_actions))
+        return rl::fail(RL_ERR_BAD_ARG, "rl_rollout_actions: bad argument");
+    if (n_cars == 0) return RL_OK;
+    const int64_t total = n_cars * n_actions;
+    if ((total + 255) / 256 > 0x7fffffffLL) return rl::fail(RL_ERR_BAD_ARG, "rl_rollout_actions: too many actions for one call");
+    rl::DeviceGuard guard(device);
+    if (!guard.ok) return rl::fail(RL_ERR_NO_DEVICE, "rl_rollout_actions: bad device index");
+    rollout_actions_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        d_actions, n_cars, n_actions, seed, stream_id, car_offset, speed_lo, speed_hi, steer_lo, steer_hi);
     RL_CUDA(cudaGetLastError());
     return RL_OK;
 }

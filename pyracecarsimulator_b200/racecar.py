@@ -135,17 +135,39 @@ class BatchedCar:
                                                   _current_stream_ptr(self.device)), "scan_crash")
         return first, ranges
 
+    # ---- the random action schedule of MCTS.rollout, drawn on the device ----
+    def random_actions(self, n_cars, n_actions, seed=42, stream_id=0, car_offset=0, speed_range=None,
+                       steer_range=None):
+        """(n_cars, n_actions, 2) float64 CUDA tensor of (speed, steer) targets, the device-side
+        counterpart of scripts/mcts.py:216-222 (steer ~ U(-max_steer_ang, max_steer_ang), then
+        speed ~ U(0, max_speed), one pair per 10 steps).  Counter-based Philox4x32-10: the value for
+        (seed, stream_id, car_offset + car, action) does not depend on batch shape or GPU count."""
+        import torch
+        cfg = dict(zip(CAR_PARAM_ORDER, self.params))
+        s_lo, s_hi = speed_range if speed_range is not None else (0.0, cfg["max_speed"])
+        a_lo, a_hi = steer_range if steer_range is not None else (-cfg["max_steer_ang"], cfg["max_steer_ang"])
+        out = torch.empty((int(n_cars), int(n_actions), 2), dtype=torch.float64, device=f"cuda:{self.device}")
+        _native.check(_native.lib().rl_rollout_actions(out.data_ptr(), int(n_cars), int(n_actions), int(seed),
+                                                       int(stream_id), int(car_offset), float(s_lo), float(s_hi),
+                                                       float(a_lo), float(a_hi), self.device,
+                                                       _current_stream_ptr(self.device)), "random_actions")
+        return out
+
     # ---- MCTS.rollout for many cars ----
     def rollout(self, marcher: PyRayMarchingGPU, states, actions, steps, fov, action_every=10, dt=0.01,
-                lidar_pose=False, scan_dist_to_base=0.275):
+                lidar_pose=False, scan_dist_to_base=0.275, seed=42, stream_id=0, car_offset=0):
         """``states`` (N, 11) float64 CUDA (updated in place), ``actions`` (N, ceil(steps/action_every), 2)
-        float64 CUDA with (speed, steer) targets.  Returns dict(crash_index int32 (N,), reward float64 (N,),
+        float64 CUDA with (speed, steer) targets, or ``None`` to draw the reference's random schedule on
+        the device (:meth:`random_actions` with ``seed``/``stream_id``/``car_offset``; returned under
+        ``"actions"``).  Returns dict(crash_index int32 (N,), reward float64 (N,),
         poses float32 (steps, N, 3), vsum float64 (N, steps))."""
         import torch
         st = _dev_tensor(states, "states", torch.float64, self.device)
-        ac = _dev_tensor(actions, "actions", torch.float64, self.device)
         n = st.shape[0]
         n_act = (steps + action_every - 1) // action_every
+        if actions is None:
+            actions = self.random_actions(n, n_act, seed=seed, stream_id=stream_id, car_offset=car_offset)
+        ac = _dev_tensor(actions, "actions", torch.float64, self.device)
         if st.dim() != 2 or st.shape[1] != 11 or tuple(ac.shape) != (n, n_act, 2):
             raise ValueError(f"states must be (N, 11) and actions (N, {n_act}, 2)")
         dev = st.device
@@ -158,4 +180,4 @@ class BatchedCar:
                                                float(scan_dist_to_base), float(fov), crash.data_ptr(),
                                                reward.data_ptr(), poses.data_ptr(), vsum.data_ptr(),
                                                _current_stream_ptr(self.device)), "rollout")
-        return dict(crash_index=crash, reward=reward, poses=poses, vsum=vsum)
+        return dict(crash_index=crash, reward=reward, poses=poses, vsum=vsum, actions=actions)

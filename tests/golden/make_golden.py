@@ -103,8 +103,14 @@ def car():
                         first_safe_ray=first_crash_ray)
 
 
+def philox():
+    """Frozen head of the default rollout action schedule (seed 42, stream 0): 8 cars x 5 actions."""
+    np.save(os.path.join(OUT, "philox_seed42.npy"), oracle.rollout_actions(8, 5, seed=42))
+
+
 if __name__ == "__main__":
     colombia()
     car()
+    philox()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -174,6 +174,43 @@ def test_fused_rollout_vs_oracle(orc, car, col, lidar_pose):
     assert np.all(got_idx[got_idx < 0] == -(steps + 1))
 
 
+def test_device_action_schedule_is_the_oracles_bit_for_bit(orc, car):
+    """rl_rollout_actions (Philox4x32-10 on the device) == oracle/philox_oracle.c, every bit, for
+    several shapes, seeds, stream ids and car offsets (including offsets beyond 2^32)."""
+    for (n, a, seed, sid, off) in [(1, 1, 42, 0, 0), (4099, 5, 42, 0, 0), (513, 7, 2**40 + 3, 9, 2**33 + 5),
+                                   (65536, 5, 42, 0, 0), (1000, 5, 0, 0xFFFFFFFF, 123456789)]:
+        got = car.random_actions(n, a, seed=seed, stream_id=sid, car_offset=off).cpu().numpy()
+        want = orc.rollout_actions(n, a, seed=seed, stream_id=sid, car_offset=off)
+        assert got.shape == (n, a, 2)
+        assert np.array_equal(got, want), (n, a, seed, sid, off)
+    got = car.random_actions(64, 3, seed=7, speed_range=(1.0, 2.0), steer_range=(-0.1, 0.3)).cpu().numpy()
+    assert np.array_equal(got, orc.rollout_actions(64, 3, seed=7, speed_range=(1.0, 2.0), steer_range=(-0.1, 0.3)))
+
+
+def test_rollout_with_device_drawn_actions(orc, car, col):
+    """actions=None: the schedule never exists on the host; the rollout equals the one fed with the
+    oracle's copy of the same schedule, and a rank's slice (car_offset) equals the whole job's."""
+    import torch
+    n, steps = 64, 50
+    start = maps.sample_free_poses(col["dist"], n, 5, col["res"], col["origin"], min_clear_px=6.0)
+    s0 = np.zeros((n, 11))
+    s0[:, :3] = start
+    s0[:, 3] = 2.0
+    st_a = torch.from_numpy(s0.copy()).cuda()
+    out_a = car.rollout(col["rm"], st_a, None, steps, FOV, seed=42)
+    acts = orc.rollout_actions(n, 5, seed=42)
+    assert np.array_equal(out_a["actions"].cpu().numpy(), acts)
+    st_b = torch.from_numpy(s0.copy()).cuda()
+    out_b = car.rollout(col["rm"], st_b, torch.from_numpy(acts).cuda(), steps, FOV)
+    for k in ("crash_index", "reward", "poses", "vsum"):
+        assert torch.equal(out_a[k], out_b[k]), k
+    assert torch.equal(st_a, st_b)
+    st_c = torch.from_numpy(s0[32:].copy()).cuda()
+    out_c = car.rollout(col["rm"], st_c, None, steps, FOV, seed=42, car_offset=32)
+    assert torch.equal(out_c["crash_index"], out_a["crash_index"][32:])
+    assert torch.equal(out_c["poses"], out_a["poses"][:, 32:])
+
+
 def test_argument_errors(car, col):
     import torch
     fresh = BatchedCar()
@@ -185,3 +222,7 @@ def test_argument_errors(car, col):
     with pytest.raises(ValueError):
         car.rollout(col["rm"], torch.zeros((4, 11), dtype=torch.float64, device="cuda"),
                     torch.zeros((4, 3, 2), dtype=torch.float64, device="cuda"), 50, FOV)
+    with pytest.raises(ValueError):
+        car.random_actions(4, 0)
+    with pytest.raises(ValueError):
+        car.random_actions(4, 5, car_offset=-1)
