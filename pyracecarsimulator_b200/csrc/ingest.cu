@@ -111,11 +111,23 @@ edt_rows_kernel(const uint16_t *__restrict__ g, int rows, int cols,
     extern __shared__ uint32_t g2[];  // cols entries
     const int r = blockIdx.x;
     const uint16_t *grow = g + (size_t)r * cols;
+    bool any_near = false;
     for (int q = threadIdx.x; q < cols; q += blockDim.x) {
         const uint32_t v = grow[q];
+        any_near |= v < G_INF;
         g2[q] = (v >= G_INF) ? G2_FAR : v * v;
     }
-    __syncthreads();
+    // A row whose every column is G_INF has no occupied cell within reach in any column (an empty
+    // map, or obstacles further than 65534 rows away): skip the outward scans, which would
+    // otherwise walk the whole row for every cell.
+    if (!__syncthreads_or(any_near)) {
+        for (int q = threadIdx.x; q < cols; q += blockDim.x) {
+            const size_t o = (size_t)r * cols + q;
+            dist2[o] = RL_DIST2_INF;
+            dist[o] = sqrtf(1e20f);
+        }
+        return;
+    }
     const int last = cols - 1;
     for (int q = threadIdx.x; q < cols; q += blockDim.x) {
         uint32_t best = g2[q];

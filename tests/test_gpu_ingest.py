@@ -77,6 +77,21 @@ def test_single_far_obstacle_long_reach(orc):
     assert np.array_equal(omap.dist2(), orc.edt_exact(occ))
 
 
+def test_empty_large_map_is_cheap_and_all_infinite():
+    """A map without any occupied cell: every distance is sqrt(1e20) and the row
+    pass must not walk the whole row for every cell (rows without a reachable column exit early)."""
+    n = 4096
+    omap = range_libc.PyOMap(np.zeros((n, n), dtype=bool))
+    assert np.all(omap.dist2() == 0x3FFFFFFF)
+    assert np.all(omap.dist() == np.float32(1e10))
+    assert omap.ingest_ms < 20.0, omap.ingest_ms
+    rm = range_libc.PyRayMarchingGPU(omap, 300)
+    ins = np.array([[10.0, 10.0, 0.3], [100.0, 50.0, -2.0]], dtype=np.float32)
+    outs = np.zeros(2, dtype=np.float32)
+    rm.calc_range_many(ins, outs)
+    assert np.all(outs == np.float32(300.0))     # resolution 1: max_range px == metres
+
+
 def test_large_map_exact_integer_edt(orc):
     # above 2896 px/side the float transform is not provably exact: the target is the exact
     # integer EDT (SURVEY.md A.3); report how many cells the float restatement disagrees on
