@@ -42,10 +42,13 @@ def test_config4_fused_rollout_full_size(orc, colombia, colombia_scan):
     s0 = np.zeros((n, 11))
     s0[:, :3] = start
     s0[:, 3] = 2.0
-    actions = np.stack([rng.uniform(0, 7.0, (n, 5)), rng.uniform(-0.4189, 0.4189, (n, 5))], axis=2)
-    d_actions = torch.from_numpy(actions).cuda()
+    # action schedule as SURVEY.md 8d fixes it: scripts/mcts.py:216-222 from Philox, seed 42, drawn on
+    # the device; the oracle's copy of the same schedule drives the CPU check below
+    actions = orc.rollout_actions(n, 5, seed=42)
     st = torch.from_numpy(s0.copy()).cuda()
-    out = car.rollout(rm, st, d_actions, steps, FOV)
+    out = car.rollout(rm, st, None, steps, FOV, seed=42)
+    d_actions = out["actions"]
+    assert np.array_equal(d_actions.cpu().numpy(), actions)
     idx = out["crash_index"].cpu().numpy()
     assert np.all((idx == -(steps + 1)) | ((idx >= 0) & (idx < steps)))
     st2 = torch.from_numpy(s0.copy()).cuda()
