@@ -82,3 +82,64 @@ def test_sharded_scan_matches_single_process(world, n_poses, gather):
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     res = dict(q.get(timeout=5) for _ in range(world))
     assert res == {r: True for r in range(world)}
+
+
+def _rollout_worker(rank, world, port, n_cars, q):
+    """ShardedRollout with a CPU stand-in for BatchedCar.rollout: the oracle's vehicle model driven
+    by the oracle's copy of the device action schedule, crash = first step whose speed target
+    exceeds a bound (any deterministic function of the GLOBAL car index would do)."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle
+        from pyracecarsimulator_b200.sharded import ShardedRollout
+        steps, every = 30, 10
+        p = oracle.car_params()
+
+        def rollout(states, car_offset, steps_, seed, stream_id):
+            n = states.shape[0]
+            acts = oracle.rollout_actions(n, (steps_ + every - 1) // every, seed=seed, stream_id=stream_id,
+                                          car_offset=car_offset)
+            crash = np.full(n, -(steps_ + 1), np.int32)
+            reward = np.zeros(n)
+            for c in range(n):
+                s = states[c].numpy().copy()
+                vs = []
+                for i in range(steps_):
+                    oracle.car_step(p, s, acts[c, i // every, 0], acts[c, i // every, 1], 0.01)
+                    vs.append(s[3])
+                    if crash[c] < 0 and acts[c, i // every, 0] > 6.0:
+                        crash[c] = i
+                reward[c] = sum(vs[:crash[c]]) if crash[c] >= 0 else sum(vs)
+            return torch.from_numpy(crash), torch.from_numpy(reward)
+
+        rng = np.random.default_rng(9)
+        s0 = np.zeros((n_cars, 11))
+        s0[:, :3] = rng.uniform(-1, 1, (n_cars, 3))
+        s0[:, 3] = 2.0
+        states = torch.from_numpy(s0)
+        sr = ShardedRollout(rollout, torch.device("cpu"))
+        got_c, got_r = sr.rollout(states, steps, seed=42)
+        want_c, want_r = rollout(states.clone(), 0, steps, 42, 0)       # the whole job in one process
+        ok = torch.equal(got_c, want_c) and torch.equal(got_r, want_r) and torch.equal(states, torch.from_numpy(s0))
+        loc_c, loc_r = sr.rollout(states, steps, seed=42, gather="none")
+        lo, hi = shard_bounds(n_cars, world, rank)
+        ok = ok and torch.equal(loc_c, want_c[lo:hi]) and torch.equal(loc_r, want_r[lo:hi])
+        ok = ok and bool((want_c >= 0).any()) == (n_cars > 8 or bool((want_c >= 0).any()))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_cars", [(2, 37), (3, 10), (2, 1), (2, 0)])
+def test_sharded_rollout_matches_single_process(world, n_cars):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rollout_worker, args=(r, world, port, n_cars, q)) for r in range(world)]
+    [p.start() for p in procs]
+    [p.join(120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    res = dict(q.get(timeout=5) for _ in range(world))
+    assert res == {r: True for r in range(world)}
