@@ -4,7 +4,9 @@
         --master-port 29555 tests/multigpu_check.py
 
 Every rank builds its replica of the map, then ShardedScanner's three NCCL gather modes and the fused
-peer-memory gather are compared bit for bit with the single-GPU scan of the whole batch."""
+peer-memory gather are compared bit for bit with the single-GPU scan of the whole batch, and
+ShardedRollout (cars sharded, device-drawn actions per global car, gather of crash index + reward)
+with the single-GPU rollout of all cars."""
 import os
 import sys
 
@@ -14,7 +16,9 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pyracecarsimulator_b200 import maps, range_libc  # noqa: E402
-from pyracecarsimulator_b200.sharded import ShardedScanner, gpu_march_fn, shard_bounds  # noqa: E402
+from pyracecarsimulator_b200.racecar import BatchedCar  # noqa: E402
+from pyracecarsimulator_b200.sharded import (ShardedRollout, ShardedScanner, gpu_march_fn, gpu_rollout_fn,  # noqa: E402
+                                             shard_bounds)
 
 
 def main():
@@ -46,6 +50,22 @@ def main():
         ok = ok and all(checks)
         if rank == 0:
             print(f"n={n}: all={checks[0]} root={checks[1]} none={checks[2]} fused={checks[3]}")
+    # fused rollout, cars sharded (config 4 shape, reduced): 1001 / 5 / 1 cars x 30 steps x 270 beams
+    car = BatchedCar(device=local)
+    car.setCarEdgeDistances(R, -fov / 2.0, fov / R, 0.275)
+    sr = ShardedRollout(gpu_rollout_fn(car, rm, fov), dev)
+    for n in (1001, 5, 1):
+        s0 = np.zeros((n, 11))
+        s0[:, :3] = maps.sample_free_poses(omap.dist(), n, 77 + n, y.resolution, y.origin, min_clear_px=6.0)
+        s0[:, 3] = 2.0
+        states = torch.from_numpy(s0)
+        whole = car.rollout(rm, states.to(dev).clone(), None, 30, fov, seed=42)      # all cars on this GPU
+        got_c, got_r = sr.rollout(states, 30, seed=42)
+        checks = [torch.equal(got_c, whole["crash_index"]), torch.equal(got_r, whole["reward"])]
+        ok = ok and all(checks)
+        if rank == 0:
+            print(f"rollout n={n}: crash_index={checks[0]} reward={checks[1]} "
+                  f"({int((whole['crash_index'] >= 0).sum())} cars crash)")
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
