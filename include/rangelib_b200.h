@@ -223,6 +223,16 @@ RL_API int32_t rl_follow_gap(const float *d_scans, int64_t num_scans, int32_t nu
                              float max_distance, float max_angle, float angle_inc, float *d_out,
                              void *stream);
 
+/* ---- caller-owned host buffers ---- */
+/* The *_host entry points use page-locked buffers in place (ranges are stored straight into `outs` by  */
+/* the kernel; no staging copy) and stage pageable ones through pinned memory owned by the marcher.    */
+/* A caller that reuses its numpy-style buffers (the reference allocates them once:                     */
+/* scripts/scan_simulator.py:32-40, scripts/two_player/scan.py:51-53) can page-lock them once with      */
+/* rl_host_register and release them with rl_host_unregister BEFORE freeing the memory.  *was_pinned    */
+/* is set to 1 when the range was page-locked already (nothing registered, do not unregister).          */
+RL_API int32_t rl_host_register(int32_t device, void *ptr, int64_t bytes, int32_t *was_pinned);
+RL_API int32_t rl_host_unregister(int32_t device, void *ptr);
+
 /* ---- measurement support (not on the product path) ---- */
 /* Throughput, in GB/s at 4 bytes per gather, of independent random 4-byte gathers from a    */
 /* `buffer_bytes` L2-resident buffer: the denominator of the L2-gather roofline.             */

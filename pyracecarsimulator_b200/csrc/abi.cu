@@ -32,4 +32,32 @@ int32_t rl_device_count(int32_t *count)
     return RL_OK;
 }
 
+// Page-lock a caller-owned host range so the *_host entry points can use it in place (ranges stored
+// straight into it by the kernel, inputs copied from it without staging).  Nothing is registered when
+// the range is page-locked already (*was_pinned = 1: the caller must not unregister it).
+int32_t rl_host_register(int32_t device, void *ptr, int64_t bytes, int32_t *was_pinned)
+{
+    if (!ptr || bytes <= 0) return rl::fail(RL_ERR_BAD_ARG, "rl_host_register: bad argument");
+    rl::DeviceGuard guard(device);
+    if (!guard.ok) return rl::fail(RL_ERR_NO_DEVICE, "rl_host_register: no such device");
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) == cudaSuccess && a.type != cudaMemoryTypeUnregistered) {
+        if (was_pinned) *was_pinned = 1;
+        return a.type == cudaMemoryTypeHost ? RL_OK : rl::fail(RL_ERR_BAD_ARG, "rl_host_register: not a host pointer");
+    }
+    cudaGetLastError();
+    if (was_pinned) *was_pinned = 0;
+    RL_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    return RL_OK;
+}
+
+int32_t rl_host_unregister(int32_t device, void *ptr)
+{
+    if (!ptr) return rl::fail(RL_ERR_BAD_ARG, "rl_host_unregister: null pointer");
+    rl::DeviceGuard guard(device);
+    if (!guard.ok) return rl::fail(RL_ERR_NO_DEVICE, "rl_host_unregister: no such device");
+    RL_CUDA(cudaHostUnregister(ptr));
+    return RL_OK;
+}
+
 }  // extern "C"

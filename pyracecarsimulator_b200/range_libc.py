@@ -12,7 +12,11 @@ CUDA tensors (device pointers, enqueued on the current torch stream, no host cop
 """
 from __future__ import annotations
 
+import atexit
+import collections
 import ctypes as C
+import os
+import threading
 
 import numpy as np
 
@@ -30,6 +34,92 @@ def _is_torch(a) -> bool:
 def _current_stream_ptr(device_index: int) -> int:
     import torch
     return int(torch.cuda.current_stream(device_index).cuda_stream)
+
+
+class _HostRegistry:
+    """Page-locks the numpy buffers a caller passes again and again.
+
+    The reference allocates its scan buffers once and reuses them for every call
+    (scripts/scan_simulator.py:32-40, scripts/two_player/scan.py:51-53).  A pageable ``outs`` costs a
+    staging copy of every range on every call; a page-locked one is written in place by the kernel.
+    So the SECOND time the same (address, size) shows up it is registered with ``rl_host_register``
+    and stays registered; the registry keeps a reference to the array, so its memory cannot be freed
+    while it is page-locked.  Only arrays whose memory numpy itself owns are taken, at most
+    ``MAX_ENTRIES`` of them and ``MAX_BYTES`` in total, nothing is ever evicted behind a caller's back;
+    :func:`release_host_buffers` (or interpreter exit) unregisters everything.  ``RL_HOST_REGISTER=0``
+    disables it.
+    """
+    MIN_BYTES = 1 << 20
+    MAX_ENTRIES = 8
+    MAX_BYTES = 1 << 30
+
+    def __init__(self):
+        self._lock = threading.Lock()
+        self._seen = collections.OrderedDict()    # (ptr, nbytes) -> sightings
+        self._reg = collections.OrderedDict()     # (ptr, nbytes) -> (array, device)
+        self._skip = set()
+        self.enabled = os.environ.get("RL_HOST_REGISTER", "1") != "0"
+
+    @staticmethod
+    def _numpy_owns(a) -> bool:
+        while isinstance(a, np.ndarray) and a.base is not None:
+            a = a.base
+        return isinstance(a, np.ndarray) and bool(a.flags["OWNDATA"])
+
+    def note(self, a: np.ndarray, device: int) -> None:
+        if not self.enabled or a.nbytes < self.MIN_BYTES:
+            return
+        key = (int(a.ctypes.data), int(a.nbytes))
+        with self._lock:
+            if key in self._reg or key in self._skip:
+                return
+            n = self._seen.pop(key, 0) + 1
+            if n < 2:
+                self._seen[key] = n
+                while len(self._seen) > 64:
+                    self._seen.popitem(last=False)
+                return
+            total = sum(k[1] for k in self._reg)
+            lo, hi = key[0], key[0] + key[1]
+            overlaps = any(k[0] < hi and lo < k[0] + k[1] for k in self._reg)
+            if (len(self._reg) >= self.MAX_ENTRIES or total + key[1] > self.MAX_BYTES or overlaps
+                    or not self._numpy_owns(a)):
+                self._remember_skip(key)
+                return
+            was = C.c_int32(0)
+            rc = _native.lib().rl_host_register(int(device), key[0], key[1], C.byref(was))
+            if rc != _native.RL_OK or was.value:
+                self._remember_skip(key)      # already page-locked by someone else, or the driver refused
+                return
+            self._reg[key] = (a, int(device))
+
+    def _remember_skip(self, key):
+        if len(self._skip) > 256:
+            self._skip.clear()
+        self._skip.add(key)
+
+    def registered_bytes(self) -> int:
+        with self._lock:
+            return sum(k[1] for k in self._reg)
+
+    def release(self) -> None:
+        with self._lock:
+            if _native._lib is not None:
+                for (ptr, _), (_, device) in self._reg.items():
+                    _native._lib.rl_host_unregister(device, ptr)
+            self._reg.clear()
+            self._seen.clear()
+            self._skip.clear()
+
+
+_HOST_REGISTRY = _HostRegistry()
+atexit.register(_HOST_REGISTRY.release)
+
+
+def release_host_buffers() -> None:
+    """Unregister every numpy buffer the library has page-locked (see :class:`_HostRegistry`).  Call
+    it only when no scan call is in flight on another thread."""
+    _HOST_REGISTRY.release()
 
 
 class _Buf:
@@ -55,6 +145,7 @@ class _Buf:
             self.on_device = False
             self.ptr = int(a.ctypes.data)
             self.shape = a.shape
+            _HOST_REGISTRY.note(a, device)
         else:
             raise ValueError(f"{name}: expected a numpy array or torch tensor, got {type(a).__name__}")
         self.keep = a

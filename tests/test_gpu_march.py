@@ -206,6 +206,53 @@ def test_torch_device_tensors_match_host_path(big):
         big["rm"].calc_range_fan(dp.double(), do, FOV, 1080)
 
 
+def test_reused_numpy_buffers_get_page_locked_and_results_do_not_change(big):
+    """Plain (pageable) numpy buffers passed twice are registered by the shim and then written in place
+    by the kernel; a first-time buffer goes through the staged path.  Same ranges either way, including
+    the 2-arg row-per-ray form whose INPUT block is the large one."""
+    import time
+    reg = range_libc._HOST_REGISTRY
+    range_libc.release_host_buffers()
+    n = 400
+    poses = maps.sample_free_poses(big["dist"], n, 77, big["res"], big["origin"])
+    want = big["orc"].calc_range_fan(poses, 1080, FOV, threads=0)
+    outs = np.zeros(n * 1080, np.float32)                      # 1.7 MB, pageable
+    times = []
+    for i in range(4):
+        outs[:] = -1.0
+        t0 = time.perf_counter()
+        big["rm"].calc_range_fan(poses, outs, FOV, 1080)
+        times.append(time.perf_counter() - t0)
+        assert np.array_equal(outs, want), i
+        assert (reg.registered_bytes() > 0) == (i >= 1)          # registered on the second sighting
+    assert reg.registered_bytes() == outs.nbytes
+    view = outs[: 200 * 1080]                                     # a shorter view of registered memory: not re-registered
+    view[:] = -1.0
+    big["rm"].calc_range_fan(poses[:200], view, FOV, 1080)
+    assert np.array_equal(view, want[: 200 * 1080]) and reg.registered_bytes() == outs.nbytes
+    # 2-arg form: (N, 3) rows in, N ranges out
+    rows = np.zeros((n * 1080, 3), np.float32)                    # 5.2 MB input block
+    inc = np.float32(FOV) / np.float32(1080)
+    ang = (np.arange(1080, dtype=np.float32) * inc + np.float32(-0.5) * np.float32(FOV)).astype(np.float32)
+    rows[:, 0] = np.repeat(poses[:, 0], 1080)
+    rows[:, 1] = np.repeat(poses[:, 1], 1080)
+    rows[:, 2] = (poses[:, 2][:, None] + ang[None, :]).astype(np.float32).ravel()
+    want2 = big["orc"].calc_range_many(rows, threads=0)
+    o2 = np.zeros(n * 1080, np.float32)
+    for i in range(3):
+        o2[:] = -1.0
+        big["rm"].calc_range_many(rows, o2)
+        assert np.array_equal(o2, want2), i
+    assert reg.registered_bytes() == outs.nbytes + rows.nbytes + o2.nbytes
+    range_libc.release_host_buffers()
+    assert reg.registered_bytes() == 0
+    outs[:] = -1.0
+    big["rm"].calc_range_fan(poses, outs, FOV, 1080)            # pageable again: staged path
+    assert np.array_equal(outs, want)
+    range_libc.release_host_buffers()
+    print("pageable outs, call times (ms):", [round(t * 1e3, 3) for t in times])
+
+
 def test_rotated_origin_map(orc):
     # non-zero origin yaw exercises the world->grid rotation (A.4)
     rng = np.random.default_rng(8)
