@@ -13,6 +13,7 @@ namespace rl {
 
 void set_error(const std::string &msg);
 int32_t fail(int32_t code, const std::string &msg);
+bool host_registered_by_lib(const void *p);   // inside a range page-locked by rl_host_register
 
 #define RL_CUDA(expr)                                                                          \
     do {                                                                                       \

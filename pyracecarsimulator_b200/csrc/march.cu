@@ -266,8 +266,10 @@ int32_t host_pipeline(rl_marcher *m, const float *ins, int64_t in_stride_floats,
         // Zero-copy output: when the caller's buffer is page-locked (mapped under unified addressing) the
         // march kernel stores its ranges straight into it over PCIe -- no device->host copy to wait for,
         // the transfer overlaps the march warp by warp.  RL_HOST_ZEROCOPY=0 falls back to the staged path.
+        // Buffers page-locked by rl_host_register (pageable memory pinned after the fact) take the copy-engine
+        // pipeline below instead: kernel stores into them measured 604 us against 411 us for the DMA.
         static const bool zero_copy_ok = [] { const char *e = std::getenv("RL_HOST_ZEROCOPY"); return !(e && e[0] == '0'); }();
-        if (out_pinned && zero_copy_ok) {
+        if (out_pinned && zero_copy_ok && !rl::host_registered_by_lib(dst)) {
             float *d_alias = nullptr;
             if (cudaHostGetDevicePointer((void **)&d_alias, dst, 0) == cudaSuccess && d_alias) {
                 RL_CUDA(cudaMemcpyAsync(m->d_in, src, (size_t)c * in_floats * sizeof(float), cudaMemcpyHostToDevice, st[0]));

@@ -44,6 +44,22 @@ def child():
     t_d2h = loop(lambda: h.copy_(d_out, non_blocking=True))
     dp = torch.from_numpy(poses).cuda()
     t_k = loop(lambda: rm.calc_range_fan(dp, d_out, 4.71, B))
+    if os.environ.get("RL_PROBE_PAGEABLE"):
+        # plain numpy buffers (what a caller of the raw range_libc API passes): first call = staged through the
+        # marcher's pinned memory + memcpy; from the second sighting on the buffer is page-locked by the shim
+        import numpy as np
+        outs = np.zeros(P * B, np.float32)
+        t0 = time.perf_counter(); rm.calc_range_fan(poses, outs, 4.71, B); t_first = (time.perf_counter() - t0) * 1e6
+        t0 = time.perf_counter(); rm.calc_range_fan(poses, outs, 4.71, B); t_second = (time.perf_counter() - t0) * 1e6
+        t_rest = loop(lambda: rm.calc_range_fan(poses, outs, 4.71, B), 20)
+        range_libc.release_host_buffers()
+        os.environ["RL_HOST_REGISTER"] = "0"
+        range_libc._HOST_REGISTRY.enabled = False
+        t_staged = loop(lambda: rm.calc_range_fan(poses, outs, 4.71, B), 20)
+        print(f"pageable numpy outs: first call {t_first:.0f} us (staged), second {t_second:.0f} us (includes cudaHostRegister), "
+              f"then {t_rest:.0f} us per call = {P * B / t_rest / 1e3:.2f} Grays/s; registration disabled: {t_staged:.0f} us per call "
+              f"= {P * B / t_staged / 1e3:.2f} Grays/s")
+        return
     print(f"subchunks={os.environ.get('RL_HOST_SUBCHUNKS', 'default')}: scanMany {t_sim:.0f} us, raw API {t_api:.0f} us, "
           f"bare pinned D2H {t_d2h:.0f} us, kernel {t_k:.0f} us -> e2e {P * B / t_sim / 1e3:.2f} Grays/s")
 
@@ -51,6 +67,8 @@ def child():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child()
+    elif len(sys.argv) > 1 and sys.argv[1] == "pageable":
+        subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=dict(os.environ, RL_PROBE_PAGEABLE="1"))
     else:
         for n in ("1", "2", "3", "4", "6", "8", "12"):
             env = dict(os.environ, RL_HOST_SUBCHUNKS=n)
