@@ -293,6 +293,20 @@ def run_native(args, rank, world, local_rank):
     e2e_s = time.perf_counter() - t0
     clocks = sampler.result()
 
+    # ---- the same call with plain (pageable) numpy buffers, as a user of the raw range_libc API passes them:
+    # first call staged, later calls into the array the shim page-locked on its second sighting ----
+    np_out = np.zeros(n_rays, dtype=np.float32)
+    np_poses = [np.array(pose_sets[i % n_sets], dtype=np.float32) for i in range(2)]
+    for i in range(3):
+        rm.calc_range_fan(np_poses[i % 2], np_out, FOV, B)
+    np_steps = max(3, min(K, 20))
+    t0 = time.perf_counter()
+    for i in range(np_steps):
+        rm.calc_range_fan(np_poses[i % 2], np_out, FOV, B)
+        checksum += float(np_out[0])
+    np_s = time.perf_counter() - t0
+    range_libc.release_host_buffers()
+
     # ---- the call MCTS actually makes on this batch: checkCollisionMany (scan + isCrashed), host poses in,
     # one int back -- scan and crash test fused, the ranges never leave the GPU ----
     from pyracecarsimulator_b200.racecar import BatchedCar
@@ -446,6 +460,10 @@ def run_native(args, rank, world, local_rank):
                     "h2d_bytes_per_step": P * 12, "d2h_bytes_per_step": n_rays * 4, "steps": e2e_steps,
                     "api": "ScanSimulator2D.scanMany(host poses) -> host ranges (pinned), per rank",
                     "pinned_d2h_gbs": d2h_gbs,
+                    "numpy_pageable_buffers": {"value": n_rays * np_steps / np_s, "unit": "rays/s per GPU",
+                                               "ms_per_call": np_s / np_steps * 1e3,
+                                               "api": "PyRayMarchingGPU.calc_range_fan(np.ndarray poses, np.zeros outs): the "
+                                                      "caller's array is page-locked on its second sighting (rl_host_register)"},
                     "pcie_bound_rays_per_s": world * d2h_gbs * 1e9 / 4.0},
             "e2e_fused_crash": {"value": n_rays * e2e_steps / fused_s, "unit": "nominal rays/s per GPU",
                                 "ms_per_call": fused_s / e2e_steps * 1e3, "first_crash_index": crash_idx,
