@@ -211,6 +211,39 @@ def test_rollout_with_device_drawn_actions(orc, car, col):
     assert torch.equal(out_c["poses"], out_a["poses"][:, 32:])
 
 
+def test_rollout_is_cuda_graph_capturable(orc, car, col):
+    """The device-pointer entry points only enqueue kernels on the caller's stream (no allocation, no
+    synchronisation, the L2 access-policy window travels as a launch attribute), so an MCTS loop can
+    capture action draw + rollout + scans + crash test into one CUDA graph and replay it."""
+    import torch
+    n, steps = 256, 30
+    start = maps.sample_free_poses(col["dist"], n, 8, col["res"], col["origin"], min_clear_px=6.0)
+    s0 = np.zeros((n, 11))
+    s0[:, :3] = start
+    s0[:, 3] = 2.0
+    d_s0 = torch.from_numpy(s0).cuda()
+    eager_states = d_s0.clone()
+    eager = car.rollout(col["rm"], eager_states, None, steps, FOV, seed=7)
+    states = d_s0.clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                       # warm-up outside capture, as torch recommends
+        car.rollout(col["rm"], states, None, steps, FOV, seed=7)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    states.copy_(d_s0)
+    with torch.cuda.graph(g):
+        out = car.rollout(col["rm"], states, None, steps, FOV, seed=7)
+    for _ in range(3):                                  # replay: same inputs -> same outputs
+        states.copy_(d_s0)
+        out["crash_index"].fill_(12345)
+        g.replay()
+        torch.cuda.synchronize()
+        for k in ("crash_index", "reward", "poses", "vsum", "actions"):
+            assert torch.equal(out[k], eager[k]), k
+        assert torch.equal(states, eager_states)
+
+
 def test_argument_errors(car, col):
     import torch
     fresh = BatchedCar()
