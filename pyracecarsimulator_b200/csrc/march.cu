@@ -48,7 +48,8 @@ march_many_kernel(MarchParams P, const float *__restrict__ ins, float *__restric
 // ---- one thread per ray over the flat (pose, beam) index space: lanes run over adjacent beams ----
 // Measured on B200 (tools/tune_march): this finest-grained mapping beats warp-per-pose, beam
 // segments per warp, persistent work queues and multi-ray-per-lane variants; the march is bound
-// by L2 sector throughput and the hardware CTA scheduler is the cheapest load balancer.
+// by instruction issue and the latency of its dependent loads (profiles/r01_ncu_full_summary.md),
+// and the hardware CTA scheduler is the cheapest load balancer.
 // FAN:   beam j heads theta + fmaf(j, fov/num_beams, -fov/2)   (fork's 4-arg calc_range_many)
 // !FAN:  beam a heads theta + angles[a]                        (calc_range_repeat_angles)
 // Peer output: the fused march + all-gather writes every range straight into the gathered buffer
