@@ -216,6 +216,11 @@ RL_API int32_t rl_rollout_actions(double *d_actions, int64_t n_cars, int32_t n_a
                                   uint32_t stream_id, int64_t car_offset, double speed_lo, double speed_hi,
                                   double steer_lo, double steer_hi, int32_t device, void *stream);
 
+/* The value MCTS.rollout returns for a node (scripts/mcts.py:240-245):                               */
+/* d_value[c] = d_reward[c] / |d_node_action[c]| (IEEE division, as numpy does it).                    */
+RL_API int32_t rl_rollout_value(const double *d_reward, const double *d_node_action, int64_t n_cars,
+                                double *d_value, int32_t device, void *stream);
+
 /* FollowGap(ws, max_distance, max_angle, angle_inc).eval(scan, num_rays) for `num_scans` scans at */
 /* once (followgap/followgap.hpp:104-129; caller scripts/mcts.py:262-267): d_scans is             */
 /* (num_scans, num_rays) fp32 ranges in metres, d_out[s] the steering angle.  num_rays >= 10.      */

@@ -73,6 +73,7 @@ SIGNATURES = {
     "rl_scan_crash": (_i32, [_vp, _vp, _vp, _i64, _i32, _f, _vp, _vp, _vp]),
     "rl_rollout": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _d, _i32, _d, _f, _vp, _vp, _vp, _vp, _vp]),
     "rl_rollout_actions": (_i32, [_vp, _i64, _i32, C.c_uint64, C.c_uint32, _i64, _d, _d, _d, _d, _i32, _vp]),
+    "rl_rollout_value": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp]),
     "rl_follow_gap": (_i32, [_vp, _i64, _i32, _f, _f, _f, _vp, _vp]),
     "rl_host_register": (_i32, [_i32, _vp, _i64, C.POINTER(_i32)]),
     "rl_host_unregister": (_i32, [_i32, _vp]),

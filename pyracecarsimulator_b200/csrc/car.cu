@@ -215,6 +215,14 @@ __global__ void finalize_first_kernel(int32_t *first, int64_t groups, int poses_
     }
 }
 
+// The value MCTS.rollout returns for a node (scripts/mcts.py:240-245): sum(rewards[:index]) / abs(node.action).
+__global__ void rollout_value_kernel(const double *__restrict__ reward, const double *__restrict__ node_action,
+                                     int64_t n, double *__restrict__ value)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n) value[c] = __ddiv_rn(reward[c], fabs(node_action[c]));
+}
+
 // Car::isCrashed over ranges that already exist: ray i of pose k of group g.
 __global__ void __launch_bounds__(256)
 crash_from_rays_kernel(const float *__restrict__ rays, const double *__restrict__ edge, int64_t total,
@@ -421,6 +429,21 @@ RL_API int32_t rl_scan_crash(rl_marcher *m, rl_car *car, const float *d_poses, i
         march_crash_kernel<false, false><<<blocks_for(total, 256), 256, 0, s>>>(
             P, d_poses, car->d_edge, total, car->num_rays, poses_per_group, groups, fov, fov / (float)car->num_rays, car->p.crash_thresh, d_first, nullptr);
     finalize_first_kernel<<<blocks_for(groups, 256), 256, 0, s>>>(d_first, groups, poses_per_group, nullptr, nullptr);
+    RL_CUDA(cudaGetLastError());
+    return RL_OK;
+}
+
+// d_value[c] = d_reward[c] / |d_node_action[c]|: what MCTS.rollout returns for the node whose action was
+// node_action (scripts/mcts.py:240-245; a zero action gives +-inf or nan exactly as numpy's division does).
+RL_API int32_t rl_rollout_value(const double *d_reward, const double *d_node_action, int64_t n_cars,
+                                double *d_value, int32_t device, void *stream)
+{
+    if (n_cars < 0 || (n_cars > 0 && (!d_reward || !d_node_action || !d_value)))
+        return rl::fail(RL_ERR_BAD_ARG, "rl_rollout_value: bad argument");
+    if (n_cars == 0) return RL_OK;
+    rl::DeviceGuard guard(device);
+    if (!guard.ok) return rl::fail(RL_ERR_NO_DEVICE, "rl_rollout_value: bad device index");
+    rollout_value_kernel<<<blocks_for(n_cars, 256), 256, 0, (cudaStream_t)stream>>>(d_reward, d_node_action, n_cars, d_value);
     RL_CUDA(cudaGetLastError());
     return RL_OK;
 }

@@ -155,12 +155,14 @@ class BatchedCar:
 
     # ---- MCTS.rollout for many cars ----
     def rollout(self, marcher: PyRayMarchingGPU, states, actions, steps, fov, action_every=10, dt=0.01,
-                lidar_pose=False, scan_dist_to_base=0.275, seed=42, stream_id=0, car_offset=0):
+                lidar_pose=False, scan_dist_to_base=0.275, seed=42, stream_id=0, car_offset=0, node_action=None):
         """``states`` (N, 11) float64 CUDA (updated in place), ``actions`` (N, ceil(steps/action_every), 2)
         float64 CUDA with (speed, steer) targets, or ``None`` to draw the reference's random schedule on
         the device (:meth:`random_actions` with ``seed``/``stream_id``/``car_offset``; returned under
         ``"actions"``).  Returns dict(crash_index int32 (N,), reward float64 (N,),
-        poses float32 (steps, N, 3), vsum float64 (N, steps))."""
+        poses float32 (steps, N, 3), vsum float64 (N, steps)); with ``node_action`` ((N,) float64 CUDA, the
+        action of the node each rollout starts from) also ``value = reward / abs(node_action)``, what
+        ``MCTS.rollout`` returns (scripts/mcts.py:240-245)."""
         import torch
         st = _dev_tensor(states, "states", torch.float64, self.device)
         n = st.shape[0]
@@ -180,4 +182,12 @@ class BatchedCar:
                                                float(scan_dist_to_base), float(fov), crash.data_ptr(),
                                                reward.data_ptr(), poses.data_ptr(), vsum.data_ptr(),
                                                _current_stream_ptr(self.device)), "rollout")
-        return dict(crash_index=crash, reward=reward, poses=poses, vsum=vsum, actions=actions)
+        out = dict(crash_index=crash, reward=reward, poses=poses, vsum=vsum, actions=actions)
+        if node_action is not None:
+            na = _dev_tensor(node_action, "node_action", torch.float64, self.device)
+            if na.numel() != n:
+                raise ValueError("node_action must be (N,)")
+            out["value"] = torch.empty(n, dtype=torch.float64, device=dev)
+            _native.check(_native.lib().rl_rollout_value(reward.data_ptr(), na.data_ptr(), n, out["value"].data_ptr(),
+                                                         self.device, _current_stream_ptr(self.device)), "rollout value")
+        return out

@@ -205,6 +205,12 @@ def test_rollout_with_device_drawn_actions(orc, car, col):
     for k in ("crash_index", "reward", "poses", "vsum"):
         assert torch.equal(out_a[k], out_b[k]), k
     assert torch.equal(st_a, st_b)
+    # the node value MCTS.rollout returns: reward / abs(node.action), same bits as numpy's division
+    na = np.random.default_rng(3).uniform(-0.41, 0.41, n)
+    st_v = torch.from_numpy(s0.copy()).cuda()
+    out_v = car.rollout(col["rm"], st_v, None, steps, FOV, seed=42, node_action=torch.from_numpy(na).cuda())
+    assert torch.equal(out_v["reward"], out_a["reward"])
+    assert np.array_equal(out_v["value"].cpu().numpy(), out_a["reward"].cpu().numpy() / np.abs(na))
     st_c = torch.from_numpy(s0[32:].copy()).cuda()
     out_c = car.rollout(col["rm"], st_c, None, steps, FOV, seed=42, car_offset=32)
     assert torch.equal(out_c["crash_index"], out_a["crash_index"][32:])
