@@ -1678,6 +1678,150 @@ __global__ void __launch_bounds__(128) k_v21(Args a, Lean q)
     a.outs[i] = __fmul_rn(rl::march_ray<false>(a.P, g.y, g.x, dx, dy, st, f0), a.P.w.scale);
 }
 
+// ---------------------------------------------------------------- V22 (third session): unit-step cooperative tail.
+// After HEAD lockstep steps (the product's loop) the rays of a warp that are still marching are served by the
+// WHOLE warp, finished lanes included: G = 32, 16, 8 or 4 lanes per ray (1, 2, 3-4, 5+ rays; at most 8 rays per
+// round, the lowest lanes first).  Lane k of a group samples at t + k -- the parameter the ray reaches after k
+// steps of exactly 1 px, which is what a creeping ray takes (61 % of the steps beyond the 32nd on the bench map,
+// in runs of 12): for t >= 16 the sequence t, t+1, (t+1)+1, ... equals fl(t + k) bit for bit (adds inside a
+// binade are exact; the single rounding at a binade crossing commutes with adding integers), so no chain of
+// dependent adds is needed.  A ballot finds the first sample of the group that does not continue with a unit
+// step; that lane decides the ray's new state.  One memory round trip per run of unit steps instead of one per step.
+template <int HEAD>
+__device__ __forceinline__ bool march_head(const MarchParams &P, float x0, float y0, float dx, float dy,
+                                           const rl::FirstSample &f0, float &t_out, float &res)
+{
+    res = P.max_range;
+    if (!f0.inside || !(dx == dx) || !(dy == dy)) return false;
+    if (f0.d <= 0.0f) {
+        const float xd = __fsub_rn((float)f0.px, x0), yd = __fsub_rn((float)f0.py, y0);
+        res = sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+        return false;
+    }
+    float t = fmaxf(__fmul_rn(f0.d, 0.999f), 1.0f);
+    if (!(t < P.max_range)) return false;
+    int px, py, it = 1;
+    float d;
+    for (;;) {
+        px = __float2int_rz(fmaf(dx, t, x0));
+        py = __float2int_rz(fmaf(dy, t, y0));
+        if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) return false;
+        d = __ldg(P.dist + (px * P.cols + py));
+        t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+        if (d <= 0.0f || !(t < P.max_range)) break;
+        if (++it == HEAD) { t_out = t; return true; }
+    }
+    if (d <= 0.0f) {
+        const float xd = __fsub_rn((float)px, x0), yd = __fsub_rn((float)py, y0);
+        res = sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+    }
+    return false;
+}
+
+// MAXG: largest number of rays served per round (1, 2, 4 or 8)
+// PLAIN: while more than PLAIN rays of the warp are marching, every one of them takes an ordinary step of its own
+// (lockstep, as in the product loop); the cooperative rounds start once PLAIN or fewer are left (0: always cooperate).
+template <int MAXG, int PLAIN = 0>
+__device__ __forceinline__ void coop_unit_tail(const MarchParams &P, float x0, float y0, float dx, float dy, float &t,
+                                               float &res, bool running)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned m = __ballot_sync(0xffffffffu, running);
+    while (m) {
+        const int ma = __popc(m);
+        if (PLAIN > 0 && ma > PLAIN) {
+            if (running) {
+                const int px = __float2int_rz(fmaf(dx, t, x0)), py = __float2int_rz(fmaf(dy, t, y0));
+                if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) { res = P.max_range; running = false; }
+                else {
+                    const float d = __ldg(P.dist + (px * P.cols + py));
+                    const float nt = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+                    if (d <= 0.0f) {
+                        const float xd = __fsub_rn((float)px, x0), yd = __fsub_rn((float)py, y0);
+                        res = sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+                        running = false;
+                    } else if (!(nt < P.max_range)) { res = P.max_range; running = false; }
+                    else t = nt;
+                }
+            }
+            m = __ballot_sync(0xffffffffu, running);
+            continue;
+        }
+        int lg = ma <= 1 ? 0 : (ma == 2 ? 1 : (ma <= 4 ? 2 : 3));   // log2(groups)
+        if ((1 << lg) > MAXG) lg = MAXG == 1 ? 0 : (MAXG == 2 ? 1 : (MAXG == 4 ? 2 : 3));
+        const int ng = 1 << lg;                     // groups this round
+        const int G = 32 >> lg;                     // lanes per group
+        const int g = lane >> (5 - lg);             // my group (0 when lg == 0)
+        const int k = lane & (G - 1);
+        // owner of group g: the (g+1)-th lowest running lane
+        unsigned mm = m;
+        int owner = 0;
+        bool has = false;
+#pragma unroll
+        for (int gg = 0; gg < MAXG; ++gg) {
+            if (gg < ng && mm) {
+                const int o = __ffs(mm) - 1;
+                if (gg == g) { owner = o; has = true; }
+                mm &= mm - 1;
+            }
+        }
+        const float ox0 = __shfl_sync(0xffffffffu, x0, owner), oy0 = __shfl_sync(0xffffffffu, y0, owner);
+        const float odx = __shfl_sync(0xffffffffu, dx, owner), ody = __shfl_sync(0xffffffffu, dy, owner);
+        const float ot = __shfl_sync(0xffffffffu, t, owner);
+        const float tk = __fadd_rn(ot, (float)k);               // == k sequential unit steps (ot >= 16)
+        const bool live = tk < P.max_range;                    // k = 0: true by invariant
+        const int px = __float2int_rz(fmaf(odx, tk, ox0)), py = __float2int_rz(fmaf(ody, tk, oy0));
+        const bool inb = (unsigned)px < (unsigned)P.rows && (unsigned)py < (unsigned)P.cols;
+        float d = 1.0f;
+        if (has && live && inb) d = __ldg(P.dist + (px * P.cols + py));
+        const float sk = fmaxf(__fmul_rn(d, 0.999f), 1.0f);
+        const float nt = __fadd_rn(tk, sk);
+        // what this sample decides if it is the first of its group that does not continue with a unit step
+        int st = 0;                                            // 0: continue from nt, 1: finished with `r`
+        float r = P.max_range;
+        if (!inb) st = 1;
+        else if (d <= 0.0f) {
+            st = 1;
+            const float xd = __fsub_rn((float)px, ox0), yd = __fsub_rn((float)py, oy0);
+            r = sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+        } else if (!(nt < P.max_range)) st = 1;
+        const bool unit_go = live && st == 0 && sk == 1.0f;      // the next lane's parameter is this ray's next one
+        const unsigned bad = __ballot_sync(0xffffffffu, !unit_go);
+        // the owner reads the verdict of the deciding lane of ITS group
+        const int myrank = __popc(m & ((1u << lane) - 1u));
+        const bool served = running && myrank < ng;
+        const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << ((myrank & (ng - 1)) * G);
+        const unsigned gb = bad & gmask;
+        int src = served ? (gb ? (__ffs(gb) - 1) : ((myrank & (ng - 1)) * G + G - 1)) : (int)lane;
+        const int st_o = __shfl_sync(0xffffffffu, st, src);
+        const float nt_o = __shfl_sync(0xffffffffu, nt, src), r_o = __shfl_sync(0xffffffffu, r, src);
+        const bool live_o = __shfl_sync(0xffffffffu, (int)live, src) != 0;
+        if (served) {
+            // a deciding lane that is not live cannot happen: the lane before it would have failed nt < max_range
+            if (st_o == 0 && live_o) t = nt_o;
+            else { res = r_o; running = false; }
+        }
+        m = __ballot_sync(0xffffffffu, running);
+    }
+}
+
+template <int HEAD, int MAXG, int PLAIN = 0>
+__global__ void __launch_bounds__(128, 16) k_v22(Args a, Lean q)
+{
+    const unsigned i = blockIdx.x * 128u + threadIdx.x;
+    const unsigned total = (unsigned)a.num_poses * a.num_beams;
+    const bool valid = i < total;
+    float x0 = 0.f, y0 = 0.f, dx = 0.f, dy = 0.f, t = 0.f, res = 0.f;
+    bool running = false;
+    if (valid) {
+        ray_setup_fan(a, q, i, x0, y0, dx, dy);
+        const rl::FirstSample f0 = rl::first_sample(a.P, x0, y0);
+        running = march_head<HEAD>(a.P, x0, y0, dx, dy, f0, t, res);
+    }
+    if (__any_sync(0xffffffffu, running)) coop_unit_tail<MAXG, PLAIN>(a.P, x0, y0, dx, dy, t, res, running);
+    if (valid) a.outs[i] = __fmul_rn(res, a.P.w.scale);
+}
+
 // ---------------------------------------------------------------- harness
 static std::vector<char> slurp(const std::string &path)
 {
@@ -1990,6 +2134,15 @@ int main(int argc, char **argv)
             R.run("v21 lean trig", [&] { k_v21<<<b3, 128>>>(a, q); });
             R.run("product-like again", [&] { k_product_like<<<b3, 128>>>(a, q); });
             R.run("v21 lean trig again", [&] { k_v21<<<b3, 128>>>(a, q); });
+            return 0;
+        }
+        if (argc > 3 && !strcmp(argv[3], "v22")) {
+            R.run("product-like (reference of this table)", [&] { k_product_like<<<b3, 128>>>(a, q); }, true);
+#define V22(HEAD, MAXG) R.run("v22 unit-step coop tail: head" #HEAD " maxgroups" #MAXG, [&] { k_v22<HEAD, MAXG><<<b3, 128>>>(a, q); });
+            V22(32, 8) V22(32, 4) V22(32, 2) V22(32, 1) V22(24, 8) V22(24, 4) V22(48, 8) V22(48, 4) V22(20, 8) V22(64, 8)
+#define V22P(HEAD, MAXG, PLAIN) R.run("v22 head" #HEAD " maxgroups" #MAXG ", plain steps while > " #PLAIN " rays", [&] { k_v22<HEAD, MAXG, PLAIN><<<b3, 128>>>(a, q); });
+            V22P(32, 4, 4) V22P(32, 2, 2) V22P(32, 1, 1) V22P(20, 4, 4) V22P(20, 2, 2) V22P(20, 1, 1) V22P(24, 8, 8)
+            R.run("product-like again", [&] { k_product_like<<<b3, 128>>>(a, q); });
             return 0;
         }
         if (argc > 3 && !strcmp(argv[3], "v16")) {
