@@ -66,8 +66,15 @@ typedef enum rl_status {
     RL_ERR_OOM = -4        /* host or device allocation failed                  */
 } rl_status;
 
-/* marcher flags (none defined yet: the only mode is the bit-exact one) */
+/* marcher flags.  The arithmetic has one mode, the bit-exact one (fp32 distance field): a narrower  */
+/* (fp16 / u16) field was measured and rejected, see DESIGN.md section 3.                            */
 #define RL_FLAG_DEFAULT 0u
+/* Do not pin the distance field in L2: by default rl_marcher_create raises the device-wide          */
+/* persisting-L2 carve-out (cudaLimitPersistingL2CacheSize) to the size of the field and every march */
+/* launch carries an access-policy window over it; rl_marcher_destroy of the last such marcher on a  */
+/* device un-pins the lines and restores the previous limit.  An embedding application that manages  */
+/* the carve-out itself passes this flag.                                                            */
+#define RL_FLAG_NO_L2_WINDOW 1u
 
 /* dist2 value of a cell from which no occupied cell is reachable (empty map) */
 #define RL_DIST2_INF 0x3fffffff
@@ -121,6 +128,26 @@ RL_API int32_t rl_map_destroy(rl_map *map);
 RL_API int32_t rl_marcher_create(const rl_map *map, float max_range_px, uint32_t flags, rl_marcher **out);
 RL_API int32_t rl_marcher_destroy(rl_marcher *m);
 
+/* Pipelined launches.  A march has no data dependence on the march before it, but in stream order it    */
+/* cannot start until that one has drained, and the drain -- a few hundred warps finishing 100-280-step  */
+/* rays one dependent load at a time -- is a third of a launch (profiles/r01_timeline.md).  Callers that  */
+/* issue scans back to back (scripts/mcts.py:118-122) can let consecutive device-pointer calls overlap:   */
+/*   RL_PIPELINE_STREAMS  calls alternate between two streams owned by the marcher.  Each launch waits    */
+/*       for everything enqueued on `stream` before the call (so its inputs are ready) but not for the    */
+/*       previous march; `stream` is made to wait for the PREVIOUS call's completion only.  Contract: the */
+/*       outputs of a call are valid in `stream` order after the NEXT march call on this marcher, or      */
+/*       after rl_marcher_join(m, stream); a call must not read what the call before it writes.           */
+/*   RL_PIPELINE_PDL      calls stay on `stream` and are launched with programmatic stream serialization: */
+/*       a march may start once every CTA of the preceding march has STARTED.  Same contract, and the     */
+/*       outputs of a call are valid after the second-next call or any non-march work on `stream`.        */
+/* _host entry points and the *_allgather calls are not affected.  Not capturable into a CUDA graph      */
+/* unless rl_marcher_join precedes the end of the capture.                                               */
+#define RL_PIPELINE_OFF 0
+#define RL_PIPELINE_STREAMS 1
+#define RL_PIPELINE_PDL 2
+RL_API int32_t rl_marcher_set_pipelined(rl_marcher *m, int32_t mode);
+RL_API int32_t rl_marcher_join(rl_marcher *m, void *stream);
+
 /* one (x, y, theta) row per ray: outs[i] = range(ins[i]) */
 RL_API int32_t rl_calc_range_many(rl_marcher *m, const float *d_ins, float *d_outs, int64_t num_rays_total,
                            void *stream);
@@ -153,12 +180,22 @@ RL_API int32_t rl_peer_free(int32_t device, void *d_ptr);
 /* (peer_bufs is a HOST array of device pointers as mapped in this process).  Ranks synchronise  */
 /* afterwards with any stream-ordered collective before reading.  With RL_GATHER_MULTICAST      */
 /* peer_bufs[0] is an NVLS multicast address bound to all `world` buffers: one multimem.st per    */
-/* range, replicated by the NVSwitch.                                                            */
+/* range, replicated by the NVSwitch.  When rank*slot_rays is a multiple of 4 the ranges of a CTA    */
+/* leave as 16-byte stores (a quarter of the NVLink packets).  Reuse: a faster rank's NEXT call      */
+/* starts storing into every GPU's buffer at once, so either barrier before the call as well or     */
+/* alternate between two sets of buffers (pyracecarsimulator_b200.sharded.PeerGather does the latter). */
 #define RL_GATHER_MULTICAST 1u
 RL_API int32_t rl_calc_range_fan_allgather(rl_marcher *m, const float *d_poses, int64_t pose_stride_rows,
                                            void *const *peer_bufs, int32_t world, int32_t rank,
                                            int64_t slot_rays, int64_t num_poses, int32_t num_rays,
                                            float fov, uint32_t flags, void *stream);
+
+/* The same for calc_range_repeat_angles (the particle-filter shape, BASELINE.json configs[2]):       */
+/* slot `rank` of every gathered buffer receives outs[i*num_angles + a] of this rank's poses.         */
+RL_API int32_t rl_calc_range_repeat_angles_allgather(rl_marcher *m, const float *d_poses, const float *d_angles,
+                                                     void *const *peer_bufs, int32_t world, int32_t rank,
+                                                     int64_t slot_rays, int64_t num_poses, int32_t num_angles,
+                                                     uint32_t flags, void *stream);
 
 /* Number of distance-field loads ("march steps") the last *_host call performed, when the */
 /* marcher was asked to count them (rl_marcher_count_steps(m, 1)); used by the roofline.    */
@@ -243,6 +280,13 @@ RL_API int32_t rl_host_unregister(int32_t device, void *ptr);
 /* `buffer_bytes` L2-resident buffer: the denominator of the L2-gather roofline.             */
 RL_API int32_t rl_gather_bandwidth(int32_t device, int64_t buffer_bytes, int32_t rounds, int32_t iters,
                                    float *gbytes_per_s);
+
+/* Random FULL-SECTOR reads from a `buffer_bytes` L2-resident buffer (each 32-byte sector requested   */
+/* once per warp instruction, every byte used, L1 bypassed): 10^9 sectors per second.  x 32 B is the   */
+/* L2 -> SM bandwidth a random-access reader can reach; the march's ncu lts__t_sectors per second are  */
+/* reported as a fraction of it (bench.py roofline.l2).                                                */
+RL_API int32_t rl_l2_sector_bandwidth(int32_t device, int64_t buffer_bytes, int32_t rounds, int32_t iters,
+                                      float *gsectors_per_s);
 
 /* Demote all persisting L2 lines to normal.  The march launches pin the distance field in L2 with an  */
 /* access-policy window (it survives unrelated traffic between calls); a benchmark that wants a truly  */

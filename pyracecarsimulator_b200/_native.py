@@ -19,6 +19,8 @@ RL_ERR_CUDA = -2
 RL_ERR_NO_DEVICE = -3
 RL_ERR_OOM = -4
 RL_FLAG_DEFAULT = 0
+RL_FLAG_NO_L2_WINDOW = 1
+RL_PIPELINE_OFF, RL_PIPELINE_STREAMS, RL_PIPELINE_PDL = 0, 1, 2
 RL_DIST2_INF = 0x3FFFFFFF
 
 
@@ -62,6 +64,9 @@ SIGNATURES = {
     "rl_peer_close": (_i32, [_i32, _vp]),
     "rl_peer_free": (_i32, [_i32, _vp]),
     "rl_calc_range_fan_allgather": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _i64, _i64, _i32, _f, C.c_uint32, _vp]),
+    "rl_calc_range_repeat_angles_allgather": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _i64, _i32, C.c_uint32, _vp]),
+    "rl_marcher_set_pipelined": (_i32, [_vp, _i32]),
+    "rl_marcher_join": (_i32, [_vp, _vp]),
     "rl_marcher_count_steps": (_i32, [_vp, _i32]),
     "rl_marcher_last_steps": (_i32, [_vp, C.POINTER(C.c_uint64)]),
     "rl_car_create": (_i32, [_vp, _i32, C.POINTER(_vp)]),
@@ -80,6 +85,7 @@ SIGNATURES = {
     "rl_probe_sincosf": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "rl_l2_reset_persisting": (_i32, [_i32]),
     "rl_gather_bandwidth": (_i32, [_i32, _i64, _i32, _i32, C.POINTER(_f)]),
+    "rl_l2_sector_bandwidth": (_i32, [_i32, _i64, _i32, _i32, C.POINTER(_f)]),
 }
 
 
@@ -123,6 +129,13 @@ def gather_bandwidth(device: int, buffer_bytes: int, rounds: int = 64, iters: in
     """GB/s (4 B per gather) of random gathers from an L2-resident buffer of this size."""
     v = _f()
     check(lib().rl_gather_bandwidth(device, buffer_bytes, rounds, iters, C.byref(v)), "gather_bandwidth")
+    return float(v.value)
+
+
+def l2_sector_bandwidth(device: int, buffer_bytes: int, rounds: int = 64, iters: int = 10) -> float:
+    """10^9 sectors/s of random full-sector (32 B) reads from an L2-resident buffer of this size."""
+    v = _f()
+    check(lib().rl_l2_sector_bandwidth(device, buffer_bytes, rounds, iters, C.byref(v)), "l2_sector_bandwidth")
     return float(v.value)
 
 

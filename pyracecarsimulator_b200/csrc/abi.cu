@@ -15,14 +15,19 @@ static thread_local std::string g_last_error;
 static std::mutex g_reg_mutex;
 static std::map<uintptr_t, uintptr_t> g_registered;
 
-bool host_registered_by_lib(const void *p)
+int host_registered_range(const void *p, size_t bytes)
 {
     std::lock_guard<std::mutex> lock(g_reg_mutex);
-    const uintptr_t a = (uintptr_t)p;
+    const uintptr_t a = (uintptr_t)p, b = a + bytes;
     auto it = g_registered.upper_bound(a);
-    if (it == g_registered.begin()) return false;
-    --it;
-    return a < it->second;
+    if (it != g_registered.begin()) {
+        auto prev = it;
+        --prev;
+        if (a < prev->second) return b <= prev->second ? 1 : -1;
+    }
+    // starts outside every registration: does it run into the next one?
+    if (it != g_registered.end() && it->first < b) return -1;
+    return 0;
 }
 
 void set_error(const std::string &msg) { g_last_error = msg; }

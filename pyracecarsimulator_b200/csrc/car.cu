@@ -16,12 +16,7 @@
 
 #include "glibc_trig.cuh"
 #include "march.cuh"
-
-struct rl_marcher;
-namespace rl {
-const MarchParams &marcher_params(const rl_marcher *m);
-int marcher_device(const rl_marcher *m);
-}  // namespace rl
+#include "marcher.h"
 
 struct CarParams {
     double wb, fc, h_cg, l_f, l_r, cs_f, cs_r, mass, i_z, crash_thresh, width, length;
@@ -40,7 +35,7 @@ namespace {
 
 constexpr double K_THRESH = 0.5, ST_THRESH = 0.53, GRAV = 9.81;
 constexpr double REF_PI = 3.145;  // sic: racecar/include/racecar.hpp:117
-constexpr int NO_CRASH = 0x7fffffff;
+constexpr uint32_t NO_CRASH = 0xffffffffu;   // what cudaMemsetAsync(.., 0xFF, ..) leaves: the identity of the unsigned atomicMin
 
 __device__ __forceinline__ double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
 
@@ -113,10 +108,12 @@ __device__ __forceinline__ void store_state(double *st, const CarState &s)
 __global__ void __launch_bounds__(128)
 car_rollout_kernel(CarParams p, double *__restrict__ states, const double *__restrict__ actions,
                    int64_t n_cars, int steps, int action_every, double dt, int lidar_pose,
-                   double scan_dist, float *__restrict__ poses, double *__restrict__ vsum)
+                   double scan_dist, float *__restrict__ poses, double *__restrict__ vsum,
+                   uint32_t *__restrict__ first)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_cars) return;
+    first[c] = NO_CRASH;   // the scan kernel that follows takes the minimum crashed step into it
     CarState s = load_state(states + 11 * c);
     const int n_actions = (steps + action_every - 1) / action_every;
     const double *act = actions + 2 * n_actions * c;
@@ -194,12 +191,6 @@ rollout_actions_kernel(double *__restrict__ actions, int64_t n_cars, int n_actio
     actions[2 * i + 1] = steer;
 }
 
-__global__ void fill_i32_kernel(int32_t *p, int64_t n, int32_t v)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
-
 // first[g] : NO_CRASH -> -(poses_per_group + 1), Car::isCrashed's "no crash" value
 __global__ void finalize_first_kernel(int32_t *first, int64_t groups, int poses_per_group,
                                       const double *__restrict__ vsum, double *__restrict__ reward)
@@ -207,7 +198,7 @@ __global__ void finalize_first_kernel(int32_t *first, int64_t groups, int poses_
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= groups) return;
     int32_t f = first[g];
-    if (f == NO_CRASH) f = -(poses_per_group + 1);
+    if ((uint32_t)f == NO_CRASH) f = -(poses_per_group + 1);
     first[g] = f;
     if (reward) {   // sum(rewards[:index]) if index >= 0 else sum(rewards)   (scripts/mcts.py:240-245)
         const int upto = f < 0 ? poses_per_group : f;
@@ -226,7 +217,7 @@ __global__ void rollout_value_kernel(const double *__restrict__ reward, const do
 // Car::isCrashed over ranges that already exist: ray i of pose k of group g.
 __global__ void __launch_bounds__(256)
 crash_from_rays_kernel(const float *__restrict__ rays, const double *__restrict__ edge, int64_t total,
-                       int num_rays, int poses_per_group, double thresh, int32_t *first)
+                       int num_rays, int poses_per_group, double thresh, uint32_t *first)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -234,7 +225,7 @@ crash_from_rays_kernel(const float *__restrict__ rays, const double *__restrict_
     const int j = (int)(i - k * num_rays);
     if (((double)rays[i] - edge[j]) < thresh) {
         const int64_t g = k / poses_per_group;
-        atomicMin(first + g, (int)(k - g * poses_per_group));
+        atomicMin(first + g, (uint32_t)(k - g * poses_per_group));
     }
 }
 
@@ -243,33 +234,25 @@ crash_from_rays_kernel(const float *__restrict__ rays, const double *__restrict_
 // Pose order: group-major (pose k = g*poses_per_group + p, the scanMany layout) or step-major
 // (k = p*groups + g, used by the rollout so that a car's earlier steps are scanned -- and its crash
 // known -- long before its later steps are scheduled).
+// Launch shape: the same 128-thread CTAs, multiply-high beam index and L2 access-policy window as
+// march_pose_kernel (profiles/r01_tuning.md sections 2 and 4).  The ray index is split so that it never
+// needs a 64-bit divide: blockIdx.y/z select the OUTER unit (the step when step-major, the group when
+// group-major), blockIdx.x * 128 + thread runs over the inner_poses * num_rays rays of that unit.
 template <bool WRITE, bool STEP_MAJOR>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(rl::MARCH_CTA_THREADS)
 march_crash_kernel(rl::MarchParams P, const float *__restrict__ poses, const double *__restrict__ edge,
-                   int64_t total, int num_rays, int poses_per_group, int64_t groups, float fov, float inc,
-                   double thresh, int32_t *first, float *__restrict__ outs)
+                   uint32_t inner_rays, int num_rays, rl::FastDiv div, int64_t inner_poses, int64_t outer_count,
+                   float fov, float inc, double thresh, uint32_t *first, float *__restrict__ outs)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    int64_t k;
-    int j;
-    if (total <= 0xffffffffLL) {
-        const uint32_t k32 = (uint32_t)i / (uint32_t)num_rays;
-        k = k32;
-        j = (int)((uint32_t)i - k32 * (uint32_t)num_rays);
-    } else {
-        k = i / num_rays;
-        j = (int)(i - k * num_rays);
-    }
-    int64_t g;
-    int pose_in_group;
-    if (STEP_MAJOR) {
-        pose_in_group = (int)(k / groups);
-        g = k - (int64_t)pose_in_group * groups;
-    } else {
-        g = k / poses_per_group;
-        pose_in_group = (int)(k - g * poses_per_group);
-    }
+    asm volatile("griddepcontrol.launch_dependents;");
+    const uint32_t idx = blockIdx.x * rl::MARCH_CTA_THREADS + threadIdx.x;
+    const int64_t outer = (int64_t)blockIdx.z * gridDim.y + blockIdx.y;
+    if (idx >= inner_rays || outer >= outer_count) return;
+    const uint32_t q = num_rays >= 2 ? rl::fast_div(idx, div) : idx;   // pose inside the outer unit
+    const int j = (int)(idx - q * (uint32_t)num_rays);
+    const int64_t k = outer * inner_poses + q;
+    const int64_t g = STEP_MAJOR ? (int64_t)q : outer;
+    const uint32_t pose_in_group = STEP_MAJOR ? (uint32_t)outer : q;
     if (!WRITE && __ldcg(first + g) < pose_in_group) return;
     const float *p = poses + 3 * k;
     const float thw = __ldg(p + 2);
@@ -280,7 +263,7 @@ march_crash_kernel(rl::MarchParams P, const float *__restrict__ poses, const dou
     rl::glibc_sincosf(thg, &s, &c);
     uint32_t steps = 0;
     const float r = __fmul_rn(rl::march_ray<false>(P, gp.y, gp.x, c, s, steps, f0), P.w.scale);
-    if (WRITE) outs[i] = r;
+    if (WRITE) outs[k * num_rays + j] = r;
     if (((double)r - __ldg(edge + j)) < thresh) atomicMin(first + g, pose_in_group);
 }
 
@@ -307,6 +290,50 @@ void edge_distances(const CarParams &p, int num_rays, double min_ang, double inc
 }
 
 inline unsigned blocks_for(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+rl::FastDiv fast_div_for(int d)
+{
+    rl::FastDiv f{0, 0, (uint32_t)d};
+    if (d >= 2) {
+        int s = 1;
+        while ((1u << s) < (uint32_t)d) ++s;
+        f.magic = (uint32_t)((((uint64_t)1 << (31 + s)) + d - 1) / d);
+        f.shift = (uint32_t)(s - 1);
+    }
+    return f;
+}
+
+// outer_count units of inner_poses poses each (see march_crash_kernel)
+template <bool WRITE, bool STEP_MAJOR>
+int32_t launch_march_crash(rl_marcher *m, const rl_car *car, const float *d_poses, int64_t inner_poses,
+                           int64_t outer_count, float fov, uint32_t *d_first, float *d_ranges, cudaStream_t s,
+                           const char *who)
+{
+    const int64_t inner_rays = inner_poses * car->num_rays;
+    if (inner_rays >= ((int64_t)1 << 31) || outer_count > (int64_t)65535 * 65535)
+        return rl::fail(RL_ERR_BAD_ARG, std::string(who) + ": too many rays for one call");
+    const unsigned gy = (unsigned)(outer_count < 65535 ? outer_count : 65535);
+    const unsigned gz = (unsigned)((outer_count + gy - 1) / gy);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks_for(inner_rays, rl::MARCH_CTA_THREADS), gy, gz);
+    cfg.blockDim = dim3(rl::MARCH_CTA_THREADS);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    if (m->l2_window_bytes) {   // keep the distance field pinned in L2, as every march launch does
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = const_cast<float *>(m->P.dist);
+        attr[0].val.accessPolicyWindow.num_bytes = m->l2_window_bytes;
+        attr[0].val.accessPolicyWindow.hitRatio = m->l2_hit_ratio;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    RL_CUDA(cudaLaunchKernelEx(&cfg, march_crash_kernel<WRITE, STEP_MAJOR>, m->P, d_poses, (const double *)car->d_edge,
+                               (uint32_t)inner_rays, car->num_rays, fast_div_for(car->num_rays), inner_poses, outer_count,
+                               fov, fov / (float)car->num_rays, car->p.crash_thresh, d_first, d_ranges));
+    return RL_OK;
+}
 
 int32_t check_car(const rl_car *car, const char *who)
 {
@@ -394,9 +421,10 @@ RL_API int32_t rl_is_crashed(rl_car *car, const float *d_rays, int64_t groups, i
     rl::DeviceGuard guard(car->device);
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t total = groups * poses_per_group * car->num_rays;
-    fill_i32_kernel<<<blocks_for(groups, 256), 256, 0, s>>>(d_first, groups, NO_CRASH);
+    RL_CUDA(cudaMemsetAsync(d_first, 0xFF, (size_t)groups * sizeof(int32_t), s));   // NO_CRASH
     crash_from_rays_kernel<<<blocks_for(total, 256), 256, 0, s>>>(d_rays, car->d_edge, total, car->num_rays,
-                                                                 poses_per_group, car->p.crash_thresh, d_first);
+                                                                 poses_per_group, car->p.crash_thresh,
+                                                                 reinterpret_cast<uint32_t *>(d_first));
     finalize_first_kernel<<<blocks_for(groups, 256), 256, 0, s>>>(d_first, groups, poses_per_group, nullptr, nullptr);
     RL_CUDA(cudaGetLastError());
     return RL_OK;
@@ -413,21 +441,15 @@ RL_API int32_t rl_scan_crash(rl_marcher *m, rl_car *car, const float *d_poses, i
     if (rc != RL_OK) return rc;
     if (!m || groups < 0 || poses_per_group <= 0 || (groups > 0 && (!d_poses || !d_first)))
         return rl::fail(RL_ERR_BAD_ARG, "rl_scan_crash: bad argument");
-    if (rl::marcher_device(m) != car->device) return rl::fail(RL_ERR_BAD_ARG, "rl_scan_crash: car and marcher are on different devices");
+    if (m->map->device != car->device) return rl::fail(RL_ERR_BAD_ARG, "rl_scan_crash: car and marcher are on different devices");
     if (groups == 0) return RL_OK;
     rl::DeviceGuard guard(car->device);
     cudaStream_t s = (cudaStream_t)stream;
-    const int64_t total = groups * poses_per_group * car->num_rays;
-    if (blocks_for(total, 256) == 0 || (total + 255) / 256 > 0x7fffffffLL)
-        return rl::fail(RL_ERR_BAD_ARG, "rl_scan_crash: too many rays for one call");
-    fill_i32_kernel<<<blocks_for(groups, 256), 256, 0, s>>>(d_first, groups, NO_CRASH);
-    const rl::MarchParams &P = rl::marcher_params(m);
-    if (d_ranges)
-        march_crash_kernel<true, false><<<blocks_for(total, 256), 256, 0, s>>>(
-            P, d_poses, car->d_edge, total, car->num_rays, poses_per_group, groups, fov, fov / (float)car->num_rays, car->p.crash_thresh, d_first, d_ranges);
-    else
-        march_crash_kernel<false, false><<<blocks_for(total, 256), 256, 0, s>>>(
-            P, d_poses, car->d_edge, total, car->num_rays, poses_per_group, groups, fov, fov / (float)car->num_rays, car->p.crash_thresh, d_first, nullptr);
+    RL_CUDA(cudaMemsetAsync(d_first, 0xFF, (size_t)groups * sizeof(int32_t), s));   // NO_CRASH
+    uint32_t *first = reinterpret_cast<uint32_t *>(d_first);
+    if (d_ranges) rc = launch_march_crash<true, false>(m, car, d_poses, poses_per_group, groups, fov, first, d_ranges, s, "rl_scan_crash");
+    else rc = launch_march_crash<false, false>(m, car, d_poses, poses_per_group, groups, fov, first, nullptr, s, "rl_scan_crash");
+    if (rc != RL_OK) return rc;
     finalize_first_kernel<<<blocks_for(groups, 256), 256, 0, s>>>(d_first, groups, poses_per_group, nullptr, nullptr);
     RL_CUDA(cudaGetLastError());
     return RL_OK;
@@ -486,18 +508,19 @@ RL_API int32_t rl_rollout(rl_marcher *m, rl_car *car, double *d_states, const do
     if (!m || n_cars < 0 || steps <= 0 || action_every <= 0 ||
         (n_cars > 0 && (!d_states || !d_actions || !d_crash_index || !d_poses || !d_vsum)))
         return rl::fail(RL_ERR_BAD_ARG, "rl_rollout: bad argument");
-    if (rl::marcher_device(m) != car->device) return rl::fail(RL_ERR_BAD_ARG, "rl_rollout: car and marcher are on different devices");
+    if (m->map->device != car->device) return rl::fail(RL_ERR_BAD_ARG, "rl_rollout: car and marcher are on different devices");
     if (n_cars == 0) return RL_OK;
     rl::DeviceGuard guard(car->device);
     cudaStream_t s = (cudaStream_t)stream;
-    const int64_t total = n_cars * steps * car->num_rays;
-    if ((total + 255) / 256 > 0x7fffffffLL) return rl::fail(RL_ERR_BAD_ARG, "rl_rollout: too many rays for one call");
+    // three launches: the vehicle steps (which also reset the crash indices), the scans with the crash test
+    // as their epilogue, and a 65 536-thread decode of "no crash" + reward.  (Folding the decode into the
+    // scan kernel's last CTA would cost one same-address atomic per CTA -- 27.6 M of them at BASELINE config 4.)
+    uint32_t *first = reinterpret_cast<uint32_t *>(d_crash_index);
     car_rollout_kernel<<<blocks_for(n_cars, 128), 128, 0, s>>>(car->p, d_states, d_actions, n_cars, steps, action_every, dt,
-                                                              lidar_pose, scan_dist_to_base, d_poses, d_vsum);
-    fill_i32_kernel<<<blocks_for(n_cars, 256), 256, 0, s>>>(d_crash_index, n_cars, NO_CRASH);
-    march_crash_kernel<false, true><<<blocks_for(total, 256), 256, 0, s>>>(
-        rl::marcher_params(m), d_poses, car->d_edge, total, car->num_rays, steps, n_cars, fov, fov / (float)car->num_rays,
-        car->p.crash_thresh, d_crash_index, nullptr);
+                                                              lidar_pose, scan_dist_to_base, d_poses, d_vsum, first);
+    RL_CUDA(cudaGetLastError());
+    rc = launch_march_crash<false, true>(m, car, d_poses, n_cars, steps, fov, first, nullptr, s, "rl_rollout");
+    if (rc != RL_OK) return rc;
     finalize_first_kernel<<<blocks_for(n_cars, 256), 256, 0, s>>>(d_crash_index, n_cars, steps, d_vsum, d_reward);
     RL_CUDA(cudaGetLastError());
     return RL_OK;

@@ -13,7 +13,9 @@ namespace rl {
 
 void set_error(const std::string &msg);
 int32_t fail(int32_t code, const std::string &msg);
-bool host_registered_by_lib(const void *p);   // inside a range page-locked by rl_host_register
+// [p, p+bytes) against the ranges page-locked by rl_host_register: 1 = inside one of them, 0 = touches none,
+// -1 = starts inside one but runs past its end (only partly page-locked)
+int host_registered_range(const void *p, size_t bytes);
 
 #define RL_CUDA(expr)                                                                          \
     do {                                                                                       \

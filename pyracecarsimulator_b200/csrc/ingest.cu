@@ -9,16 +9,18 @@
 //                    cut are all pure functions of one byte, so the host folds them into the LUT
 //                    with the reference's double arithmetic), applies map_server's y-flip, writes
 //                    the occupancy byte, records the segment's first/last occupied row.
-//   edt_cols_kernel  same mapping: distance g to the nearest occupied cell in the same column
-//                    (down sweep seeded from the segments above, up sweep from those below), as
-//                    saturating u16.
-//   edt_rows_kernel  one CTA per map row with the row's g^2 staged in shared memory: each
-//                    thread takes the lower envelope min_k (k^2 + g^2[q +- k]) by an outward
-//                    scan that stops as soon as k^2 >= best, which is exact in integers and
-//                    costs O(distance) per cell; writes d^2 (int32) and sqrt_rn((float)d^2).
+//   edt_seg_scan_kernel  one thread per column: nearest occupied row above / below every segment.
+//   edt_cols_kernel  one thread per (column, segment): distance g to the nearest occupied cell in the
+//                    same column (down sweep seeded from above, up sweep from below), saturating u16.
+//   edt_rows_kernel  one CTA per map row with the row's g^2 staged in shared memory: the lower
+//                    envelope min_k (k^2 + g^2[q +- k]), by an outward scan that stops at k^2 >= best
+//                    when the row's cost bound is small and by divide and conquer over the monotone
+//                    argmin (O(W log W) per row whatever the map) otherwise; exact in integers either
+//                    way; writes d^2 (int32) and sqrt_rn((float)d^2).
 // For max(rows, cols) <= 2896 the reference's float Felzenszwalb transform returns exactly
 // this integer d^2, so the fp32 field is bit-identical to the reference's.
 #include <cmath>
+#include <cstdlib>
 #include <new>
 
 #include "common.h"
@@ -61,27 +63,44 @@ edt_classify_kernel(const uint8_t *__restrict__ src, int rows, int cols, int fli
     seg_last[(size_t)seg * cols + c] = last;
 }
 
-// Column pass, step 2: distance g (saturating u16) to the nearest occupied cell of the same column:
+// Column pass, step 2 (one thread per column, in place): seg_last[seg] becomes the last occupied row ABOVE
+// the segment (in any earlier segment), seg_first[seg] the first occupied row BELOW it.  The loads do not
+// depend on each other, so the 2 * nseg of them pipeline; searching the neighbouring segments from inside
+// the sweep kernel instead cost O(nseg) dependent loads per (column, segment) on sparse maps.
+__global__ void __launch_bounds__(128)
+edt_seg_scan_kernel(int cols, int nseg, int *__restrict__ seg_first, int *__restrict__ seg_last)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    int carry = SEG_NONE_LAST;
+#pragma unroll 8
+    for (int s2 = 0; s2 < nseg; ++s2) {
+        const int l = seg_last[(size_t)s2 * cols + c];
+        seg_last[(size_t)s2 * cols + c] = carry;
+        if (l != SEG_NONE_LAST) carry = l;
+    }
+    carry = SEG_NONE_FIRST;
+#pragma unroll 8
+    for (int s2 = nseg - 1; s2 >= 0; --s2) {
+        const int f = seg_first[(size_t)s2 * cols + c];
+        seg_first[(size_t)s2 * cols + c] = carry;
+        if (f != SEG_NONE_FIRST) carry = f;
+    }
+}
+
+// Column pass, step 3: distance g (saturating u16) to the nearest occupied cell of the same column:
 // down sweep seeded with the last occupied row above the segment, up sweep seeded with the first
 // occupied row below it.
 __global__ void __launch_bounds__(128)
 edt_cols_kernel(const uint8_t *__restrict__ occ, int rows, int cols, int nseg,
-                const int *__restrict__ seg_first, const int *__restrict__ seg_last,
+                const int *__restrict__ seg_below, const int *__restrict__ seg_above,
                 uint16_t *__restrict__ g)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int seg = blockIdx.y;
     if (c >= cols) return;
     const int r0 = seg * SEG_ROWS, r1 = min(rows, r0 + SEG_ROWS);
-    int above = SEG_NONE_LAST, below = SEG_NONE_FIRST;
-    for (int s2 = seg - 1; s2 >= 0; --s2) {
-        const int l = seg_last[(size_t)s2 * cols + c];
-        if (l != SEG_NONE_LAST) { above = l; break; }
-    }
-    for (int s2 = seg + 1; s2 < nseg; ++s2) {
-        const int f = seg_first[(size_t)s2 * cols + c];
-        if (f != SEG_NONE_FIRST) { below = f; break; }
-    }
+    const int above = seg_above[(size_t)seg * cols + c], below = seg_below[(size_t)seg * cols + c];
     uint32_t run = (above == SEG_NONE_LAST) ? G_INF : min((uint32_t)(r0 - 1 - above), G_INF);
 #pragma unroll 8
     for (int r = r0; r < r1; ++r) {
@@ -97,58 +116,168 @@ edt_cols_kernel(const uint8_t *__restrict__ occ, int rows, int cols, int nseg,
     }
 }
 
-// Row pass.  g2 in shared memory holds g^2, or G2_FAR for columns without any occupied cell;
-// G2_FAR + k^2 cannot wrap and stays above every real d^2 (<= 2 * 16384^2), so the scan needs no
-// special case for it.  Out-of-row neighbours are clamped to the row ends: the clamped candidate
-// k^2 + g2[end] is never below the true candidate (q - end)^2 + g2[end], so the minimum is
-// unchanged.  Four offsets are examined per trip (independent shared-memory loads, one exit test).
+// Row pass: d2(q) = min_k (q - k)^2 + g2[k] over the row's g^2 staged in shared memory (G2_FAR for columns
+// without any occupied cell; G2_FAR + k^2 cannot wrap and stays above every real d^2 <= 2 * 16384^2, so it
+// needs no special case).  One CTA per map row, two exact integer algorithms, chosen PER ROW:
+//
+//   outward scan        each cell looks at k = 1, 2, ... on both sides and stops as soon as k^2 >= best.
+//                       O(distance to the nearest obstacle) per cell: nothing on an indoor map, O(W) per cell
+//                       on a sparse one (a lone obstacle on an 8192^2 map is ~10^11 probes).  The scan of cell q
+//                       never goes beyond k = g[q] (best starts at g[q]^2), so sum_q min(g[q], W) bounds the
+//                       row's cost before it is run.
+//   divide and conquer  the matrix f(q, k) = (q-k)^2 + g2[k] is Monge (f(q1,k1) + f(q2,k2) <= f(q1,k2) +
+//                       f(q2,k1) for q1 < q2, k1 < k2, because -2qk is), so some argmin is monotone in q and
+//                       the argmin of a middle column splits the candidates of the columns left and right of
+//                       it.  Columns are solved level by level in bisection order -- q+1 = odd multiples of
+//                       h = T/2, T/4, ..., 1 -- each searching only [argmin(q - h), argmin(q + h)]; the ranges
+//                       of one level sum to at most W + (queries), so a row costs O(W log W) probes whatever
+//                       the map.  Ties may resolve to any argmin: the value is what is stored.
+//
+// A row takes the scan when its bound is at most SCAN_BUDGET probes per cell, the divide and conquer
+// otherwise; RL_EDT_ROWS=scan|dc forces one (tests, measurements).  Both give the same exact integers.
+// Shared-memory indices are padded by one word per 32 (sw()) so that the power-of-two strides of the
+// bisection order do not pile onto one bank.
 constexpr uint32_t G2_FAR = 0x3fffffffu;
+constexpr int ROW_THREADS = 256;
+constexpr int SCAN_BUDGET = 32;
+constexpr int ROWS_AUTO = 0, ROWS_SCAN = 1, ROWS_DC = 2;
 
-__global__ void __launch_bounds__(256)
-edt_rows_kernel(const uint16_t *__restrict__ g, int rows, int cols,
+__device__ __forceinline__ int sw(int i) { return i + (i >> 5); }
+
+__device__ __forceinline__ void dc_bounds(const uint16_t *opt, int cols, int j, int h, int &q, int &lo, int &hi)
+{
+    const int qp = (2 * j + 1) * h;          // q + 1
+    const int left = qp - h, right = qp + h; // solved at an earlier level (or outside the row)
+    q = qp - 1;
+    lo = left == 0 ? 0 : (int)opt[sw(left - 1)];
+    hi = right > cols ? cols - 1 : (int)opt[sw(right - 1)];
+}
+
+__global__ void __launch_bounds__(ROW_THREADS)
+edt_rows_kernel(const uint16_t *__restrict__ g, int rows, int cols, int log2T, int force, int budget,
                 int32_t *__restrict__ dist2, float *__restrict__ dist)
 {
-    extern __shared__ uint32_t g2[];  // cols entries
-    const int r = blockIdx.x;
+    extern __shared__ uint32_t g2[];                                     // sw(cols) words of g^2 ...
+    uint16_t *opt = reinterpret_cast<uint16_t *>(g2 + sw(cols) + 1);     // ... then sw(cols) argmins
+    __shared__ uint32_t red_v[ROW_THREADS / 32];
+    __shared__ int red_k[ROW_THREADS / 32];
+    __shared__ unsigned long long cost;
+    const int r = blockIdx.x, tid = threadIdx.x;
     const uint16_t *grow = g + (size_t)r * cols;
+    if (tid == 0) cost = 0;
+    __syncthreads();
     bool any_near = false;
-    for (int q = threadIdx.x; q < cols; q += blockDim.x) {
+    uint32_t mine = 0;
+    for (int q = tid; q < cols; q += ROW_THREADS) {
         const uint32_t v = grow[q];
         any_near |= v < G_INF;
-        g2[q] = (v >= G_INF) ? G2_FAR : v * v;
+        mine += min(v, (uint32_t)cols);
+        g2[sw(q)] = (v >= G_INF) ? G2_FAR : v * v;
     }
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if ((tid & 31) == 0) atomicAdd(&cost, (unsigned long long)mine);
     // A row whose every column is G_INF has no occupied cell within reach in any column (an empty
-    // map, or obstacles further than 65534 rows away): skip the outward scans, which would
-    // otherwise walk the whole row for every cell.
+    // map): nothing to minimise.
     if (!__syncthreads_or(any_near)) {
-        for (int q = threadIdx.x; q < cols; q += blockDim.x) {
+        for (int q = tid; q < cols; q += ROW_THREADS) {
             const size_t o = (size_t)r * cols + q;
             dist2[o] = RL_DIST2_INF;
-            dist[o] = sqrtf(1e20f);
+            dist[o] = sqrtf(1e20f);   // what the reference's INF = 1e20 transform leaves on an empty map
         }
         return;
     }
-    const int last = cols - 1;
-    for (int q = threadIdx.x; q < cols; q += blockDim.x) {
-        uint32_t best = g2[q];
-        const int reach = max(q, last - q);
-        for (int k = 1; k <= reach; k += 4) {
-            if ((uint32_t)k * (uint32_t)k >= best) break;
-            uint32_t c[8];
+    const bool scan = force == ROWS_SCAN || (force == ROWS_AUTO && cost <= (unsigned long long)budget * cols);
+    if (scan) {
+        // Out-of-row neighbours are clamped to the row ends: the clamped candidate k^2 + g2[end] is never below
+        // the true candidate (q - end)^2 + g2[end], so the minimum is unchanged.  Four offsets per trip
+        // (independent shared-memory loads, one exit test).
+        const int last = cols - 1;
+        for (int q = tid; q < cols; q += ROW_THREADS) {
+            uint32_t best = g2[sw(q)];
+            const int reach = max(q, last - q);
+            for (int k = 1; k <= reach; k += 4) {
+                if ((uint32_t)k * (uint32_t)k >= best) break;
+                uint32_t c[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int kk = k + u;
-                const uint32_t k2 = (uint32_t)kk * (uint32_t)kk;
-                c[2 * u] = k2 + g2[max(q - kk, 0)];
-                c[2 * u + 1] = k2 + g2[min(q + kk, last)];
+                for (int u = 0; u < 4; ++u) {
+                    const int kk = k + u;
+                    const uint32_t k2 = (uint32_t)kk * (uint32_t)kk;
+                    c[2 * u] = k2 + g2[sw(max(q - kk, 0))];
+                    c[2 * u + 1] = k2 + g2[sw(min(q + kk, last))];
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) best = min(best, c[u]);
             }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) best = min(best, c[u]);
+            const size_t o = (size_t)r * cols + q;
+            if (best >= G2_FAR) {
+                dist2[o] = RL_DIST2_INF;
+                dist[o] = sqrtf(1e20f);
+            } else {
+                dist2[o] = (int32_t)best;
+                dist[o] = sqrtf((float)best);
+            }
         }
+        return;
+    }
+    for (int h = 1 << (log2T - 1); h >= 1; h >>= 1) {
+        const int nq = (cols / h + 1) >> 1;   // queries of this level: (2j+1) h <= cols
+        if (nq >= ROW_THREADS) {              // a query per thread, several per thread at the bottom levels
+            for (int j = tid; j < nq; j += ROW_THREADS) {
+                int q, lo, hi;
+                dc_bounds(opt, cols, j, h, q, lo, hi);
+                uint32_t bv = 0xffffffffu;
+                int bk = lo;
+                for (int k = lo; k <= hi; ++k) {
+                    const int d = q - k;
+                    const uint32_t v = (uint32_t)(d * d) + g2[sw(k)];
+                    if (v < bv) { bv = v; bk = k; }
+                }
+                opt[sw(q)] = (uint16_t)bk;
+            }
+        } else if (nq > 0) {                  // a group of G threads per query
+            const int G = 1 << (31 - __clz(ROW_THREADS / nq));
+            const int grp = tid / G, l = tid & (G - 1);
+            const bool active = grp < nq;
+            uint32_t bv = 0xffffffffu;
+            int bk = 0, q = 0;
+            if (active) {
+                int lo, hi;
+                dc_bounds(opt, cols, grp, h, q, lo, hi);
+                bk = lo;
+                for (int k = lo + l; k <= hi; k += G) {
+                    const int d = q - k;
+                    const uint32_t v = (uint32_t)(d * d) + g2[sw(k)];
+                    if (v < bv) { bv = v; bk = k; }
+                }
+            }
+            const int W = G < 32 ? G : 32;
+            for (int o = W >> 1; o > 0; o >>= 1) {
+                const uint32_t v2 = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int k2 = __shfl_xor_sync(0xffffffffu, bk, o);
+                if (v2 < bv) { bv = v2; bk = k2; }
+            }
+            if (G <= 32) {
+                if (active && l == 0) opt[sw(q)] = (uint16_t)bk;
+            } else {
+                if ((tid & 31) == 0) { red_v[tid >> 5] = bv; red_k[tid >> 5] = bk; }
+                __syncthreads();
+                if (active && l == 0) {
+                    const int w0 = tid >> 5, nw = G >> 5;
+                    for (int w = w0 + 1; w < w0 + nw; ++w)
+                        if (red_v[w] < bv) { bv = red_v[w]; bk = red_k[w]; }
+                    opt[sw(q)] = (uint16_t)bk;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (int q = tid; q < cols; q += ROW_THREADS) {
+        const int k = opt[sw(q)], d = q - k;
+        const uint32_t best = (uint32_t)(d * d) + g2[sw(k)];
         const size_t o = (size_t)r * cols + q;
         if (best >= G2_FAR) {
             dist2[o] = RL_DIST2_INF;
-            dist[o] = sqrtf(1e20f);  // what the reference's INF = 1e20 transform leaves on an empty map
+            dist[o] = sqrtf(1e20f);
         } else {
             dist2[o] = (int32_t)best;
             dist[o] = sqrtf((float)best);
@@ -223,16 +352,27 @@ int32_t build_map(const uint8_t *src, int width, int height, int flip, const Byt
     RL_TRY(cudaMemcpy(d_src, src, n, cudaMemcpyHostToDevice));
     RL_TRY(cudaEventCreate(&e0));
     RL_TRY(cudaEventCreate(&e1));
-    const size_t smem = (size_t)width * sizeof(uint32_t);
+    const size_t padded = (size_t)width + ((size_t)width >> 5) + 2;
+    const size_t smem = padded * (sizeof(uint32_t) + sizeof(uint16_t));
+    // RL_EDT_ROWS=scan|dc forces one row algorithm (tests and measurements); default: chosen per row
+    const char *rows_env = std::getenv("RL_EDT_ROWS");
+    const int force = !rows_env ? ROWS_AUTO : (rows_env[0] == 's' ? ROWS_SCAN : (rows_env[0] == 'd' ? ROWS_DC : ROWS_AUTO));
+    int budget = SCAN_BUDGET;
+    if (const char *e = std::getenv("RL_EDT_BUDGET")) { const long v = std::atol(e); if (v >= 0 && v <= 1 << 20) budget = (int)v; }
     RL_TRY(cudaFuncSetAttribute(edt_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RL_TRY(cudaEventRecord(e0, 0));
     {
         const dim3 grid((width + 127) / 128, nseg);
         int *seg_first = d_seg, *seg_last = d_seg + (size_t)nseg * width;
         edt_classify_kernel<<<grid, 128>>>(d_src, height, width, flip, lut, m->d_occ, seg_first, seg_last);
+        edt_seg_scan_kernel<<<(width + 127) / 128, 128>>>(width, nseg, seg_first, seg_last);
         edt_cols_kernel<<<grid, 128>>>(m->d_occ, height, width, nseg, seg_first, seg_last, d_g);
     }
-    edt_rows_kernel<<<height, 256, smem>>>(d_g, height, width, m->d_dist2, m->d_dist);
+    {
+        int log2T = 1;
+        while ((1 << log2T) < width + 1) ++log2T;
+        edt_rows_kernel<<<height, ROW_THREADS, smem>>>(d_g, height, width, log2T, force, budget, m->d_dist2, m->d_dist);
+    }
     RL_TRY(cudaGetLastError());
     RL_TRY(cudaEventRecord(e1, 0));
     RL_TRY(cudaEventSynchronize(e1));

@@ -9,14 +9,19 @@
 
 #include "glibc_trig.cuh"
 #include "march.cuh"
+#include "marcher.h"
 
 namespace {
 
 using rl::GridPose;
 using rl::MarchParams;
+using rl::launch_windowed;
 
-constexpr int WARPS_PER_CTA = 4;   // 128-thread CTAs measured best (tools/tune_march)
-constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
+constexpr int CTA_THREADS = rl::MARCH_CTA_THREADS;
+
+// Programmatic dependent launch: let the next kernel in the stream start being scheduled as soon as
+// every CTA of this one has started (a no-op unless that kernel was launched with the PDL attribute).
+__device__ __forceinline__ void release_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 
 template <bool COUNT>
 __device__ __forceinline__ void flush_steps(uint32_t steps, unsigned long long *counter)
@@ -33,6 +38,7 @@ __global__ void __launch_bounds__(CTA_THREADS)
 march_many_kernel(MarchParams P, const float *__restrict__ ins, float *__restrict__ outs,
                   int64_t n, unsigned long long *counter)
 {
+    release_dependents();
     const int64_t i = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
     uint32_t steps = 0;
     if (i < n) {
@@ -55,7 +61,12 @@ march_many_kernel(MarchParams P, const float *__restrict__ ins, float *__restric
 // Peer output: the fused march + all-gather writes every range straight into the gathered buffer
 // of every GPU of the box (its own included) over NVLink, so the transfer overlaps the march ray by
 // ray instead of following it as a separate collective.
+//   OUT_LOCAL  outs[i] = r
+//   OUT_PEERS  one 4-byte store per range and peer (or one multimem.st, replicated by the NVSwitch)
+//   OUT_PEERS4 the CTA's 128 ranges are staged in shared memory and leave as 32 16-byte stores per peer
+//              (multimem.st.v4.f32 with multicast): a quarter of the NVLink packets for the same bytes
 constexpr int MAX_PEERS = 16;
+constexpr int OUT_LOCAL = 0, OUT_PEERS = 1, OUT_PEERS4 = 2;
 struct PeerOut {
     float *buf[MAX_PEERS];   // gathered buffer of each rank (peer-mapped device pointers)
     int world;
@@ -63,13 +74,38 @@ struct PeerOut {
     int64_t offset;          // this rank's slot: rank * slot_rays
 };
 
-template <bool FAN, bool COUNT, bool SMALL, bool PEERS = false>
+__device__ __forceinline__ void peer_store(const PeerOut &peers, int64_t i, float r)
+{
+    if (peers.multicast) {   // the NVSwitch replicates the store to all GPUs of the multicast group
+        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(peers.buf[0] + peers.offset + i), "f"(r)
+                     : "memory");
+    } else {
+#pragma unroll 1
+        for (int q = 0; q < peers.world; ++q) peers.buf[q][peers.offset + i] = r;
+    }
+}
+
+__device__ __forceinline__ void peer_store4(const PeerOut &peers, int64_t i, float4 v)
+{
+    if (peers.multicast) {
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(peers.buf[0] + peers.offset + i),
+                     "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                     : "memory");
+    } else {
+#pragma unroll 1
+        for (int q = 0; q < peers.world; ++q) *reinterpret_cast<float4 *>(peers.buf[q] + peers.offset + i) = v;
+    }
+}
+
+template <bool FAN, bool COUNT, bool SMALL, int OUT = OUT_LOCAL>
 __global__ void __launch_bounds__(CTA_THREADS)
 march_pose_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_stride_floats,
                   const float *__restrict__ angles, float *__restrict__ outs, int64_t num_rays_total,
                   int num_beams, rl::FastDiv div, float fov, float inc, unsigned long long *counter,
                   PeerOut peers = PeerOut{})
 {
+    release_dependents();
+    __shared__ float stage[OUT == OUT_PEERS4 ? CTA_THREADS : 1];
     const int64_t i = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
     uint32_t steps = 0;
     if (i < num_rays_total) {
@@ -93,16 +129,20 @@ march_pose_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_s
         float s, c;
         rl::glibc_sincosf(thg, &s, &c);
         const float r = __fmul_rn(rl::march_ray<COUNT>(P, g.y, g.x, c, s, steps, f0), P.w.scale);
-        if (PEERS) {
-            if (peers.multicast) {   // the NVSwitch replicates the store to all GPUs of the multicast group
-                asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(peers.buf[0] + peers.offset + i), "f"(r)
-                             : "memory");
+        if (OUT == OUT_PEERS) peer_store(peers, i, r);
+        else if (OUT == OUT_PEERS4) stage[threadIdx.x] = r;
+        else outs[i] = r;
+    }
+    if (OUT == OUT_PEERS4) {   // peers.offset is a multiple of 4 floats (checked by the host), so is the CTA's base
+        __syncthreads();
+        if (threadIdx.x < CTA_THREADS / 4) {
+            const int64_t b = (int64_t)blockIdx.x * CTA_THREADS + 4 * threadIdx.x;
+            if (b + 3 < num_rays_total) {
+                peer_store4(peers, b, *reinterpret_cast<const float4 *>(stage + 4 * threadIdx.x));
             } else {
-#pragma unroll 1
-                for (int q = 0; q < peers.world; ++q) peers.buf[q][peers.offset + i] = r;
+                for (int e = 0; e < 4; ++e)
+                    if (b + e < num_rays_total) peer_store(peers, b + e, stage[4 * threadIdx.x + e]);
             }
-        } else {
-            outs[i] = r;
         }
     }
     flush_steps<COUNT>(steps, counter);
@@ -116,26 +156,6 @@ __global__ void trig_probe_kernel(const float *__restrict__ in, float *__restric
 }
 
 }  // namespace
-
-struct rl_marcher {
-    const rl_map *map = nullptr;
-    MarchParams P{};
-    uint32_t flags = 0;
-    int sm_count = 148;
-    // host-variant staging (guarded by mu)
-    std::mutex mu;
-    cudaStream_t stream = nullptr, stream2 = nullptr;   // double-buffered H2D -> march -> D2H pipeline
-    float *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr, *d_angles = nullptr;
-    size_t cap_in = 0, cap_out = 0, cap_angles = 0;  // floats
-    // L2 persistence: the distance field is the one buffer every ray of every call re-reads, so each march
-    // launch carries an access-policy window over it (persisting hits) and it stays L2-resident between
-    // calls whatever else streams through the cache (0 = window unavailable on this device)
-    size_t l2_window_bytes = 0;
-    float l2_hit_ratio = 1.0f;
-    // optional step counter
-    bool count = false;
-    unsigned long long *d_steps = nullptr;
-};
 
 namespace rl {
 const MarchParams &marcher_params(const rl_marcher *m) { return m->P; }
@@ -157,46 +177,31 @@ int32_t ensure(float **h, float **d, size_t *cap, size_t want)
     return RL_OK;
 }
 
-bool is_pinned(const void *p)
+bool is_pinned_byte(const void *p)
 {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeHost;
 }
 
-// Launch with the distance-field access-policy window attached to this launch only (no stream or
-// device state of the caller is touched beyond the persisting-L2 carve-out set at marcher creation).
-template <typename... KArgs, typename... Args>
-cudaError_t launch_windowed(const rl_marcher *m, void (*kernel)(KArgs...), unsigned blocks, cudaStream_t s,
-                            Args &&...args)
+// Page-locked over its WHOLE extent?  A caller may hand a longer view over the start of a buffer that was
+// page-locked (by rl_host_register or by itself) for a shorter length: both ends are asked, and a range the
+// library registered must lie inside one registration.  Anything else takes the staged path.
+bool is_pinned_range(const void *p, size_t bytes)
 {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(blocks);
-    cfg.blockDim = dim3(CTA_THREADS);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    if (m->l2_window_bytes) {
-        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-        attr[0].val.accessPolicyWindow.base_ptr = const_cast<float *>(m->P.dist);
-        attr[0].val.accessPolicyWindow.num_bytes = m->l2_window_bytes;
-        attr[0].val.accessPolicyWindow.hitRatio = m->l2_hit_ratio;
-        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-    }
-    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+    if (bytes == 0) return false;
+    if (!is_pinned_byte(p) || !is_pinned_byte(static_cast<const char *>(p) + bytes - 1)) return false;
+    return rl::host_registered_range(p, bytes) >= 0;
 }
 
-int32_t launch_many(rl_marcher *m, const float *d_ins, float *d_outs, int64_t n, cudaStream_t s)
+int32_t launch_many(rl_marcher *m, const float *d_ins, float *d_outs, int64_t n, cudaStream_t s, bool pdl = false)
 {
     if (n == 0) return RL_OK;
     const int64_t blocks = (n + CTA_THREADS - 1) / CTA_THREADS;
     if (blocks > 0x7fffffffLL) return rl::fail(RL_ERR_BAD_ARG, "calc_range_many: too many rays for one call");
     unsigned long long *ctr = m->count ? m->d_steps : nullptr;
-    if (m->count) RL_CUDA(launch_windowed(m, march_many_kernel<true>, (unsigned)blocks, s, m->P, d_ins, d_outs, n, ctr));
-    else RL_CUDA(launch_windowed(m, march_many_kernel<false>, (unsigned)blocks, s, m->P, d_ins, d_outs, n, ctr));
+    if (m->count) RL_CUDA(launch_windowed(m, march_many_kernel<true>, (unsigned)blocks, s, pdl, m->P, d_ins, d_outs, n, ctr));
+    else RL_CUDA(launch_windowed(m, march_many_kernel<false>, (unsigned)blocks, s, pdl, m->P, d_ins, d_outs, n, ctr));
     RL_CUDA(cudaGetLastError());
     return RL_OK;
 }
@@ -213,9 +218,11 @@ rl::FastDiv make_fast_div(int d)
     return f;
 }
 
+// One launch of march_pose_kernel.  peers == nullptr: ranges to d_outs; otherwise to the gathered buffers.
 template <bool FAN>
 int32_t launch_pose(rl_marcher *m, const float *d_poses, int64_t stride_rows, const float *d_angles,
-                    float *d_outs, int64_t num_poses, int num_beams, float fov, cudaStream_t s)
+                    float *d_outs, int64_t num_poses, int num_beams, float fov, cudaStream_t s,
+                    bool pdl = false, const PeerOut *peers = nullptr)
 {
     if (num_poses == 0 || num_beams == 0) return RL_OK;
     const int64_t total = num_poses * num_beams;
@@ -226,12 +233,21 @@ int32_t launch_pose(rl_marcher *m, const float *d_poses, int64_t stride_rows, co
     const bool small = num_beams >= 2 && total < ((int64_t)1 << 31);
     unsigned long long *ctr = m->count ? m->d_steps : nullptr;
     const int64_t stride_floats = stride_rows * 3;
-    const PeerOut no_peers{};
-#define RL_LAUNCH(COUNT, SMALL)                                                                    \
-    RL_CUDA(launch_windowed(m, march_pose_kernel<FAN, COUNT, SMALL, false>, (unsigned)blocks, s, m->P, d_poses, \
-                            stride_floats, d_angles, d_outs, total, num_beams, div, fov, inc, ctr, no_peers))
-    if (m->count) { if (small) RL_LAUNCH(true, true); else RL_LAUNCH(true, false); }
-    else { if (small) RL_LAUNCH(false, true); else RL_LAUNCH(false, false); }
+    const PeerOut po = peers ? *peers : PeerOut{};
+#define RL_LAUNCH(COUNT, SMALL, OUT)                                                               \
+    RL_CUDA(launch_windowed(m, march_pose_kernel<FAN, COUNT, SMALL, OUT>, (unsigned)blocks, s, pdl, m->P, d_poses, \
+                            stride_floats, d_angles, d_outs, total, num_beams, div, fov, inc, ctr, po))
+    if (peers) {
+        // 16-byte stores need this rank's slot to start on a 16-byte boundary; RL_GATHER_VEC=0 forces 4-byte stores
+        static const bool vec_ok = [] { const char *e = std::getenv("RL_GATHER_VEC"); return !(e && e[0] == '0'); }();
+        const bool vec = vec_ok && (po.offset % 4) == 0;
+        if (vec) { if (small) RL_LAUNCH(false, true, OUT_PEERS4); else RL_LAUNCH(false, false, OUT_PEERS4); }
+        else { if (small) RL_LAUNCH(false, true, OUT_PEERS); else RL_LAUNCH(false, false, OUT_PEERS); }
+    } else if (m->count) {
+        if (small) RL_LAUNCH(true, true, OUT_LOCAL); else RL_LAUNCH(true, false, OUT_LOCAL);
+    } else {
+        if (small) RL_LAUNCH(false, true, OUT_LOCAL); else RL_LAUNCH(false, false, OUT_LOCAL);
+    }
 #undef RL_LAUNCH
     RL_CUDA(cudaGetLastError());
     return RL_OK;
@@ -249,13 +265,12 @@ int32_t host_pipeline(rl_marcher *m, const float *ins, int64_t in_stride_floats,
     if (units == 0 || out_floats == 0) return RL_OK;
     int64_t big = (int64_t)(HOST_CHUNK_RAYS / (size_t)out_floats);   // units per staged chunk
     if (big < 1) big = 1;
-    const bool in_pinned = in_stride_floats == in_floats && is_pinned(ins);
-    const bool out_pinned = is_pinned(outs);
+    const bool in_pinned = in_stride_floats == in_floats && is_pinned_range(ins, (size_t)units * in_floats * sizeof(float));
+    const bool out_pinned = is_pinned_range(outs, (size_t)units * out_floats * sizeof(float));
     cudaStream_t st[2] = {m->stream, m->stream2};
     for (int64_t b = 0; b < units; b += big) {
         const int64_t c = (units - b < big) ? units - b : big;
         int32_t rc = ensure(&m->h_in, &m->d_in, &m->cap_in, (size_t)c * in_floats);
-        if (rc == RL_OK) rc = ensure(&m->h_out, &m->d_out, &m->cap_out, (size_t)c * out_floats);
         if (rc != RL_OK) return rc;
         const float *src = ins + b * in_stride_floats;
         if (!in_pinned) {   // gather (strided fork layout) or stage (pageable) into pinned memory
@@ -263,16 +278,15 @@ int32_t host_pipeline(rl_marcher *m, const float *ins, int64_t in_stride_floats,
             else for (int64_t k = 0; k < c; ++k) std::memcpy(m->h_in + k * in_floats, src + k * in_stride_floats, in_floats * sizeof(float));
             src = m->h_in;
         }
-        float *dst = out_pinned ? outs + b * out_floats : m->h_out;
         // Zero-copy output: when the caller's buffer is page-locked (mapped under unified addressing) the
         // march kernel stores its ranges straight into it over PCIe -- no device->host copy to wait for,
         // the transfer overlaps the march warp by warp.  RL_HOST_ZEROCOPY=0 falls back to the staged path.
         // Buffers page-locked by rl_host_register (pageable memory pinned after the fact) take the copy-engine
         // pipeline below instead: kernel stores into them measured 604 us against 411 us for the DMA.
         static const bool zero_copy_ok = [] { const char *e = std::getenv("RL_HOST_ZEROCOPY"); return !(e && e[0] == '0'); }();
-        if (out_pinned && zero_copy_ok && !rl::host_registered_by_lib(dst)) {
+        if (out_pinned && zero_copy_ok && rl::host_registered_range(outs, (size_t)units * out_floats * sizeof(float)) == 0) {
             float *d_alias = nullptr;
-            if (cudaHostGetDevicePointer((void **)&d_alias, dst, 0) == cudaSuccess && d_alias) {
+            if (cudaHostGetDevicePointer((void **)&d_alias, outs + b * out_floats, 0) == cudaSuccess && d_alias) {
                 RL_CUDA(cudaMemcpyAsync(m->d_in, src, (size_t)c * in_floats * sizeof(float), cudaMemcpyHostToDevice, st[0]));
                 rc = launch(0, c, m->d_in, d_alias, st[0]);
                 if (rc != RL_OK) return rc;
@@ -281,6 +295,17 @@ int32_t host_pipeline(rl_marcher *m, const float *ins, int64_t in_stride_floats,
             }
             cudaGetLastError();
         }
+        // staged / copy-engine path: device ranges, plus a pinned bounce buffer only for pageable outputs
+        rc = ensure(nullptr, &m->d_out, &m->cap_out, (size_t)c * out_floats);
+        if (rc != RL_OK) return rc;
+        if (!out_pinned && m->cap_hout < (size_t)c * out_floats) {
+            cudaFreeHost(m->h_out);
+            m->h_out = nullptr;
+            m->cap_hout = 0;
+            RL_CUDA(cudaMallocHost(&m->h_out, (size_t)c * out_floats * sizeof(float)));
+            m->cap_hout = (size_t)c * out_floats;
+        }
+        float *dst = out_pinned ? outs + b * out_floats : m->h_out;
         // A few equal sub-chunks of >= 512K ranges (RL_HOST_SUBCHUNKS overrides the count, for
         // experiments): every async call costs microseconds of host time, so the pipeline is kept
         // shallow; small inputs (the fan's 12 B/pose) go up in one copy.
@@ -321,6 +346,25 @@ int32_t host_pipeline(rl_marcher *m, const float *ins, int64_t in_stride_floats,
     return RL_OK;
 }
 
+// The persisting-L2 carve-out is a device-wide limit: remember what it was before the first marcher on a
+// device raised it and put it back when the last such marcher goes.
+struct L2Carve { size_t before = 0; int users = 0; };
+std::mutex g_l2_mu;
+L2Carve g_l2[64];
+
+int32_t fill_peers(PeerOut &po, void *const *peer_bufs, int32_t world, int32_t rank, int64_t slot_rays, uint32_t flags,
+                   const char *who)
+{
+    for (int q = 0; q < world; ++q) {
+        if (!peer_bufs[q]) return rl::fail(RL_ERR_BAD_ARG, std::string(who) + ": null peer buffer");
+        po.buf[q] = static_cast<float *>(peer_bufs[q]);
+    }
+    po.world = world;
+    po.multicast = (flags & RL_GATHER_MULTICAST) ? 1 : 0;
+    po.offset = (int64_t)rank * slot_rays;
+    return RL_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -338,6 +382,7 @@ int32_t rl_marcher_create(const rl_map *map, float max_range_px, uint32_t flags,
 {
     if (!map || !out) return rl::fail(RL_ERR_BAD_ARG, "rl_marcher_create: null pointer");
     if (!(max_range_px > 0.0f)) return rl::fail(RL_ERR_BAD_ARG, "rl_marcher_create: max_range_px must be > 0");
+    if (flags & ~(uint32_t)RL_FLAG_NO_L2_WINDOW) return rl::fail(RL_ERR_BAD_ARG, "rl_marcher_create: unknown flag");
     rl::DeviceGuard guard(map->device);
     if (!guard.ok) return rl::fail(RL_ERR_CUDA, "rl_marcher_create: cudaSetDevice failed");
     rl_marcher *m = new (std::nothrow) rl_marcher();
@@ -353,18 +398,26 @@ int32_t rl_marcher_create(const rl_map *map, float max_range_px, uint32_t flags,
     m->P.max_range = max_range_px;
     m->P.w = map->world;
     cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, map->device);
-    {   // persisting-L2 carve-out large enough for the distance field (device-wide limit; only ever raised)
+    if (!(flags & RL_FLAG_NO_L2_WINDOW) && map->device < 64) {
+        // persisting-L2 carve-out large enough for the distance field: a device-wide limit, raised here and put
+        // back by rl_marcher_destroy when the last marcher that needed it goes
         int max_persist = 0, max_window = 0;
         cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, map->device);
         cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, map->device);
         const size_t field = (size_t)map->rows * map->cols * sizeof(float);
+        std::lock_guard<std::mutex> lock(g_l2_mu);
+        L2Carve &cv = g_l2[map->device];
         size_t cur = 0;
         cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
         // only when the whole field fits: pinning a fraction of a larger field measured slightly slower
-        if (max_persist > 0 && field <= (size_t)max_persist && field <= (size_t)max_window &&
-            (cur >= field || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, field) == cudaSuccess)) {
-            m->l2_window_bytes = field;
-            m->l2_hit_ratio = 1.0f;
+        if (max_persist > 0 && field <= (size_t)max_persist && field <= (size_t)max_window) {
+            if (cv.users == 0) cv.before = cur;
+            if (cur >= field || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, field) == cudaSuccess) {
+                m->l2_window_bytes = field;
+                m->l2_hit_ratio = 1.0f;
+                m->l2_limit_raised = true;
+                ++cv.users;
+            }
         }
         cudaGetLastError();
     }
@@ -387,11 +440,57 @@ int32_t rl_marcher_destroy(rl_marcher *m)
         rl::DeviceGuard guard(m->map->device);
         if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
         if (m->stream2) { cudaStreamSynchronize(m->stream2); cudaStreamDestroy(m->stream2); }
+        for (int i = 0; i < 2; ++i) {
+            if (m->pipe[i]) { cudaStreamSynchronize(m->pipe[i]); cudaStreamDestroy(m->pipe[i]); }
+            if (m->fork_ev[i]) cudaEventDestroy(m->fork_ev[i]);
+            if (m->done_ev[i]) cudaEventDestroy(m->done_ev[i]);
+        }
         cudaFreeHost(m->h_in); cudaFreeHost(m->h_out);
         cudaFree(m->d_in); cudaFree(m->d_out); cudaFree(m->d_angles); cudaFree(m->d_steps);
+        if (m->l2_limit_raised) {
+            std::lock_guard<std::mutex> lock(g_l2_mu);
+            L2Carve &cv = g_l2[m->map->device];
+            if (--cv.users == 0) {   // last user on this device: un-pin the field's lines, give the carve-out back
+                cudaCtxResetPersistingL2Cache();
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, cv.before);
+            }
+        }
+        cudaGetLastError();
     }
     rl_map_release(m->map);
     delete m;
+    return RL_OK;
+}
+
+int32_t rl_marcher_set_pipelined(rl_marcher *m, int32_t mode)
+{
+    if (!m || mode < RL_PIPELINE_OFF || mode > RL_PIPELINE_PDL)
+        return rl::fail(RL_ERR_BAD_ARG, "rl_marcher_set_pipelined: bad argument");
+    rl::DeviceGuard guard(m->map->device);
+    std::lock_guard<std::mutex> lock(m->pipe_mu);
+    if (mode == RL_PIPELINE_STREAMS && !m->pipe[0]) {
+        for (int i = 0; i < 2; ++i) {
+            RL_CUDA(cudaStreamCreateWithFlags(&m->pipe[i], cudaStreamNonBlocking));
+            RL_CUDA(cudaEventCreateWithFlags(&m->fork_ev[i], cudaEventDisableTiming));
+            RL_CUDA(cudaEventCreateWithFlags(&m->done_ev[i], cudaEventDisableTiming));
+        }
+    }
+    if (m->pipelined == RL_PIPELINE_STREAMS && mode != RL_PIPELINE_STREAMS && (m->done_pending[0] || m->done_pending[1]))
+        return rl::fail(RL_ERR_BAD_ARG, "rl_marcher_set_pipelined: call rl_marcher_join before leaving the two-stream mode");
+    m->pipelined = mode;
+    return RL_OK;
+}
+
+int32_t rl_marcher_join(rl_marcher *m, void *stream)
+{
+    if (!m) return rl::fail(RL_ERR_BAD_ARG, "rl_marcher_join: null marcher");
+    rl::DeviceGuard guard(m->map->device);
+    std::lock_guard<std::mutex> lock(m->pipe_mu);
+    for (int i = 0; i < 2; ++i) {
+        if (!m->done_pending[i]) continue;
+        RL_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, m->done_ev[i], 0));
+        m->done_pending[i] = false;
+    }
     return RL_OK;
 }
 
@@ -418,7 +517,10 @@ int32_t rl_calc_range_many(rl_marcher *m, const float *d_ins, float *d_outs, int
 {
     if (!m || n < 0 || (n > 0 && (!d_ins || !d_outs))) return rl::fail(RL_ERR_BAD_ARG, "rl_calc_range_many: bad argument");
     rl::DeviceGuard guard(m->map->device);
-    return launch_many(m, d_ins, d_outs, n, (cudaStream_t)stream);
+    rl::PipeScope ps(m, (cudaStream_t)stream);
+    const int32_t rc = launch_many(m, d_ins, d_outs, n, ps.run, ps.pdl);
+    RL_CUDA(ps.finish());
+    return rc;
 }
 
 int32_t rl_calc_range_fan(rl_marcher *m, const float *d_poses, int64_t pose_stride_rows, float *d_outs,
@@ -428,8 +530,11 @@ int32_t rl_calc_range_fan(rl_marcher *m, const float *d_poses, int64_t pose_stri
         (num_poses > 0 && (!d_poses || !d_outs)))
         return rl::fail(RL_ERR_BAD_ARG, "rl_calc_range_fan: bad argument");
     rl::DeviceGuard guard(m->map->device);
-    return launch_pose<true>(m, d_poses, pose_stride_rows, nullptr, d_outs, num_poses, num_rays, fov,
-                             (cudaStream_t)stream);
+    rl::PipeScope ps(m, (cudaStream_t)stream);
+    const int32_t rc = launch_pose<true>(m, d_poses, pose_stride_rows, nullptr, d_outs, num_poses, num_rays, fov,
+                                         ps.run, ps.pdl);
+    RL_CUDA(ps.finish());
+    return rc;
 }
 
 int32_t rl_calc_range_repeat_angles(rl_marcher *m, const float *d_poses, const float *d_angles,
@@ -439,8 +544,10 @@ int32_t rl_calc_range_repeat_angles(rl_marcher *m, const float *d_poses, const f
         (num_poses > 0 && num_angles > 0 && (!d_poses || !d_angles || !d_outs)))
         return rl::fail(RL_ERR_BAD_ARG, "rl_calc_range_repeat_angles: bad argument");
     rl::DeviceGuard guard(m->map->device);
-    return launch_pose<false>(m, d_poses, 1, d_angles, d_outs, num_poses, num_angles, 0.0f,
-                              (cudaStream_t)stream);
+    rl::PipeScope ps(m, (cudaStream_t)stream);
+    const int32_t rc = launch_pose<false>(m, d_poses, 1, d_angles, d_outs, num_poses, num_angles, 0.0f, ps.run, ps.pdl);
+    RL_CUDA(ps.finish());
+    return rc;
 }
 
 // ---- peer memory for the fused march + all-gather (one process per GPU) ----
@@ -500,31 +607,28 @@ int32_t rl_calc_range_fan_allgather(rl_marcher *m, const float *d_poses, int64_t
     if (num_poses == 0) return RL_OK;
     rl::DeviceGuard guard(m->map->device);
     PeerOut po{};
-    for (int q = 0; q < world; ++q) {
-        if (!peer_bufs[q]) return rl::fail(RL_ERR_BAD_ARG, "rl_calc_range_fan_allgather: null peer buffer");
-        po.buf[q] = static_cast<float *>(peer_bufs[q]);
-    }
-    po.world = world;
-    po.multicast = (flags & RL_GATHER_MULTICAST) ? 1 : 0;
-    po.offset = (int64_t)rank * slot_rays;
-    const int64_t total = num_poses * num_rays;
-    const int64_t blocks = (total + CTA_THREADS - 1) / CTA_THREADS;
-    if (blocks > 0x7fffffffLL) return rl::fail(RL_ERR_BAD_ARG, "rl_calc_range_fan_allgather: too many rays for one call");
-    const rl::FastDiv div = make_fast_div(num_rays);
-    const float inc = fov / (float)num_rays;
-    cudaStream_t s = (cudaStream_t)stream;
-    const int64_t stride_floats = pose_stride_rows * 3;
-    const float *no_angles = nullptr;
-    float *no_outs = nullptr;
-    unsigned long long *no_ctr = nullptr;
-    if (num_rays >= 2 && total < ((int64_t)1 << 31))
-        RL_CUDA(launch_windowed(m, march_pose_kernel<true, false, true, true>, (unsigned)blocks, s, m->P, d_poses,
-                                stride_floats, no_angles, no_outs, total, (int)num_rays, div, fov, inc, no_ctr, po));
-    else
-        RL_CUDA(launch_windowed(m, march_pose_kernel<true, false, false, true>, (unsigned)blocks, s, m->P, d_poses,
-                                stride_floats, no_angles, no_outs, total, (int)num_rays, div, fov, inc, no_ctr, po));
-    RL_CUDA(cudaGetLastError());
-    return RL_OK;
+    const int32_t rc = fill_peers(po, peer_bufs, world, rank, slot_rays, flags, "rl_calc_range_fan_allgather");
+    if (rc != RL_OK) return rc;
+    return launch_pose<true>(m, d_poses, pose_stride_rows, nullptr, nullptr, num_poses, num_rays, fov,
+                             (cudaStream_t)stream, false, &po);
+}
+
+// calc_range_repeat_angles (the particle-filter shape, BASELINE config 3) with the same fused all-gather.
+int32_t rl_calc_range_repeat_angles_allgather(rl_marcher *m, const float *d_poses, const float *d_angles,
+                                              void *const *peer_bufs, int32_t world, int32_t rank,
+                                              int64_t slot_rays, int64_t num_poses, int32_t num_angles,
+                                              uint32_t flags, void *stream)
+{
+    if (!m || !peer_bufs || world < 1 || world > MAX_PEERS || rank < 0 || rank >= world || num_poses < 0 ||
+        num_angles <= 0 || num_poses * num_angles > slot_rays || (num_poses > 0 && (!d_poses || !d_angles)))
+        return rl::fail(RL_ERR_BAD_ARG, "rl_calc_range_repeat_angles_allgather: bad argument");
+    if (num_poses == 0) return RL_OK;
+    rl::DeviceGuard guard(m->map->device);
+    PeerOut po{};
+    const int32_t rc = fill_peers(po, peer_bufs, world, rank, slot_rays, flags, "rl_calc_range_repeat_angles_allgather");
+    if (rc != RL_OK) return rc;
+    return launch_pose<false>(m, d_poses, 1, d_angles, nullptr, num_poses, num_angles, 0.0f, (cudaStream_t)stream,
+                              false, &po);
 }
 
 int32_t rl_calc_range_many_host(rl_marcher *m, const float *ins, float *outs, int64_t n)

@@ -87,13 +87,21 @@ class RacecarSimulator:
     def checkCollision(self):
         return self.car.isCrashed(np.array(self.scan, dtype=np.float32), self.num_rays, 1)
 
-    def checkCollisionMany(self, poses):
+    def checkCollisionMany(self, poses, want_ranges=False):
         """Scan ``batch_size`` poses and return the index of the first crashed one, or
-        ``-(batch_size + 1)``: one fused kernel, only 4 bytes come back."""
+        ``-(batch_size + 1)``: one fused kernel, only 4 bytes come back.
+
+        Difference from the reference: its ``scanMany`` call also leaves all ``batch_size * num_rays``
+        ranges in ``scan_simulator.output_vector_many`` (scripts/racecar_simulator_v2.py:153); nothing in
+        the reference reads them afterwards, and here poses after the first crash are not even scanned, so
+        that buffer is left untouched.  ``want_ranges=True`` restores the side effect (every pose scanned,
+        the ranges copied into ``output_vector_many``)."""
         p = np.ascontiguousarray(np.asarray(poses, dtype=np.float32)[:self.batch_size, :3])
         self._poses_dev.copy_(self._torch.from_numpy(p))
-        first, _ = self.car.scan_crash(self.scan_simulator.scan_method, self._poses_dev, 1, self.batch_size,
-                                       self.scan_fov)
+        first, ranges = self.car.scan_crash(self.scan_simulator.scan_method, self._poses_dev, 1, self.batch_size,
+                                            self.scan_fov, want_ranges=want_ranges)
+        if want_ranges:
+            self._torch.from_numpy(self.scan_simulator.output_vector_many).copy_(ranges)
         return int(first.item())
 
     def stop(self):

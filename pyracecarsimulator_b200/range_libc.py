@@ -232,7 +232,10 @@ class PyOMap:
     def isOccupied(self, x: int, y: int) -> bool:
         if x < 0 or y < 0 or x >= self._rows or y >= self._cols:
             return False
-        return bool(self.occupancy()[x, y])
+        occ = getattr(self, "_occ_host", None)
+        if occ is None:   # the map is immutable: one device->host copy serves every later query
+            occ = self._occ_host = self.occupancy()
+        return bool(occ[x, y])
 
     def error(self) -> bool:
         return False
@@ -280,8 +283,7 @@ class PyRayMarchingGPU:
         _native.check(_native.lib().rl_marcher_create(omap._h, float(max_range), int(flags), C.byref(h)),
                       type(self).__name__)
         self._h = h
-        self._one_in = np.zeros((1, 3), dtype=np.float32)
-        self._one_out = np.zeros(1, dtype=np.float32)
+        self._tls = threading.local()   # calc_range scratch, one pair per calling thread
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -290,9 +292,12 @@ class PyRayMarchingGPU:
 
     # ---- upstream API ----
     def calc_range(self, x, y, heading) -> float:
-        self._one_in[0] = (x, y, heading)
-        self.calc_range_many(self._one_in, self._one_out)
-        return float(self._one_out[0])
+        t = self._tls
+        if not hasattr(t, "one_in"):
+            t.one_in, t.one_out = np.zeros((1, 3), dtype=np.float32), np.zeros(1, dtype=np.float32)
+        t.one_in[0] = (x, y, heading)
+        self.calc_range_many(t.one_in, t.one_out)
+        return float(t.one_out[0])
 
     def calc_range_many(self, ins, outs, fov=None, num_rays=None):
         """2-arg: ``outs[i] = range(ins[i])``.  4-arg (fork): pose ``k`` is row ``k*num_rays`` of
@@ -359,6 +364,18 @@ class PyRayMarchingGPU:
         else:
             rc = L.rl_calc_range_fan_host(self._h, p.ptr, 1, o.ptr, b, num_rays, float(fov))
         _native.check(rc, "calc_range_fan")
+
+    # ---- pipelined launches (include/rangelib_b200.h: rl_marcher_set_pipelined) ----
+    def set_pipelined(self, mode=_native.RL_PIPELINE_STREAMS):
+        """Let consecutive device-tensor calls of this marcher overlap (``mode``: ``"streams"``/1, ``"pdl"``/2,
+        ``False``/0).  The ranges of a call are then valid on the current stream after the NEXT call on
+        this marcher or after :meth:`join`; a call must not consume what the call before it produces."""
+        mode = {"off": 0, "streams": 1, "pdl": 2, False: 0, True: 1, None: 0}.get(mode, mode)
+        _native.check(_native.lib().rl_marcher_set_pipelined(self._h, int(mode)), "set_pipelined")
+
+    def join(self):
+        """Make the current torch stream wait for every pipelined march issued so far."""
+        _native.check(_native.lib().rl_marcher_join(self._h, _current_stream_ptr(self.device)), "join")
 
     # ---- roofline support: count distance-field loads ----
     def count_steps(self, enable: bool = True):

@@ -34,22 +34,29 @@ class _DevicePtr:
 
 
 class PeerGather:
-    """The fused march + all-gather: one gathered-ranges buffer per GPU (``world * slot_rays`` floats)
-    mapped into every process, so that ``rl_calc_range_fan_allgather`` can store each range straight
-    into slot ``rank`` of all ``world`` buffers over NVLink while it marches (no separate collective,
-    no staging copy).  ``sync()`` is the stream-ordered barrier after which every rank may read
-    ``tensor()``.
+    """The fused march + all-gather: gathered-ranges buffers on every GPU (``world * slot_rays`` floats
+    each) mapped into every process, so that ``rl_calc_range_fan_allgather`` /
+    ``rl_calc_range_repeat_angles_allgather`` can store each range straight into slot ``rank`` of all
+    ``world`` buffers over NVLink while it marches (no separate collective, no staging copy).
+    ``sync()`` is the stream-ordered barrier after which every rank may read ``tensor()``.
+
+    Reuse: there are ``nbuf`` (default 2) sets of buffers and consecutive calls alternate between them.
+    A faster rank's next march starts storing into every GPU's buffer as soon as ITS stream gets there, so
+    with one set it could overwrite ranges a slower rank is still reading (write-after-read across ranks);
+    with two, a set is rewritten only after the barrier of the call in between, which no rank passes before
+    every rank has finished that call's march -- and a rank enqueues that march after its own consumers of
+    the earlier result.  ``tensor()`` of a call therefore stays valid until the call after next ON ANY
+    RANK; consumers must be enqueued on the marching stream (or synchronised with it) before the next call.
 
     backend "symm":  torch symmetric memory does the plumbing (allocation, rendezvous, signal-pad
-                     barrier); with ``multicast=True`` and NVLS support the kernel issues ONE
-                     ``multimem.st`` per range to the multicast address and the NVSwitch replicates it.
+                     barrier); with ``multicast=True`` and NVLS support the kernel issues
+                     ``multimem.st`` to the multicast address and the NVSwitch replicates it.
     backend "ipc":   buffers allocated by the C ABI and exchanged as CUDA IPC handles; barrier = a
                      4-byte NCCL all_reduce.  Used when symmetric memory is unavailable.
     """
 
     def __init__(self, device_index: int, slot_rays: int, group: Optional[dist.ProcessGroup] = None,
-                 backend: str = "auto", multicast: bool = True):
-        import ctypes as C
+                 backend: str = "auto", multicast: bool = True, nbuf: int = 2):
         from . import _native
         self._native = _native
         self.group = group
@@ -57,11 +64,15 @@ class PeerGather:
         self.rank = dist.get_rank(group)
         self.device_index = int(device_index)
         self.slot_rays = int(slot_rays)
+        self.nbuf = max(1, int(nbuf))
         self.flags = 0
         self._hdl = None
         self._own = None
         self._opened = []
-        n_floats = self.world * self.slot_rays
+        self._next = 0
+        self._last = 0
+        self.buf_floats = self.world * self.slot_rays
+        n_floats = self.nbuf * self.buf_floats
         if backend in ("auto", "symm"):
             try:
                 self._init_symm(n_floats, multicast)
@@ -74,9 +85,13 @@ class PeerGather:
         if self._hdl is None:
             self._init_ipc(n_floats)
             self.backend = "ipc"
+        import ctypes as C
+        # per buffer set: the `world` base pointers the kernel stores through
+        self._ptr_sets = [(C.c_void_p * self.world)(*[p + b * self.buf_floats * 4 for p in self._base_ptrs])
+                          for b in range(self.nbuf)]
+        self.ptrs = self._ptr_sets[0]
 
     def _init_symm(self, n_floats, multicast):
-        import ctypes as C
         import torch.distributed._symmetric_memory as symm_mem
         dev = torch.device("cuda", self.device_index)
         t = symm_mem.empty(n_floats, dtype=torch.float32, device=dev)
@@ -89,9 +104,9 @@ class PeerGather:
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
         if int(ok.item()) == 1:
             self.flags = 1   # RL_GATHER_MULTICAST
-            self.ptrs = (C.c_void_p * self.world)(*([mc] + ptrs[1:]))
+            self._base_ptrs = [mc] + ptrs[1:]
         else:
-            self.ptrs = (C.c_void_p * self.world)(*ptrs)
+            self._base_ptrs = ptrs
         self._view = t
         self._hdl = hdl
 
@@ -114,7 +129,7 @@ class PeerGather:
             self._native.check(L.rl_peer_open(self.device_index, buf, C.byref(p)), "rl_peer_open")
             self._opened.append(p)
             ptrs.append(p.value)
-        self.ptrs = (C.c_void_p * self.world)(*ptrs)
+        self._base_ptrs = ptrs
         self._flag = torch.zeros(1, dtype=torch.int32, device=f"cuda:{self.device_index}")
         self._view = torch.as_tensor(_DevicePtr(own.value, n_floats), device=f"cuda:{self.device_index}")
 
@@ -122,15 +137,33 @@ class PeerGather:
     def multicast(self) -> bool:
         return bool(self.flags & 1)
 
-    def tensor(self) -> torch.Tensor:
-        """This GPU's gathered buffer: (world * slot_rays,) float32, slot r = ranges of rank r."""
-        return self._view
+    def tensor(self, buf: Optional[int] = None) -> torch.Tensor:
+        """This GPU's gathered buffer of the last call (or of set ``buf``): (world * slot_rays,) float32,
+        slot r = ranges of rank r."""
+        b = self._last if buf is None else int(buf)
+        return self._view[b * self.buf_floats:(b + 1) * self.buf_floats]
 
-    def march(self, marcher, poses: torch.Tensor, fov: float, num_rays: int, stream_ptr: int):
+    def _take(self, buf):
+        b = self._next if buf is None else int(buf)
+        self._last = b
+        self._next = (b + 1) % self.nbuf
+        return self._ptr_sets[b]
+
+    def march(self, marcher, poses: torch.Tensor, fov: float, num_rays: int, stream_ptr: int,
+              buf: Optional[int] = None):
+        """Fan scan of this rank's poses into slot ``rank`` of every GPU's next buffer set."""
         n = poses.shape[0]
         self._native.check(self._native.lib().rl_calc_range_fan_allgather(
-            marcher._h, poses.data_ptr(), 1, self.ptrs, self.world, self.rank, self.slot_rays, n, int(num_rays),
+            marcher._h, poses.data_ptr(), 1, self._take(buf), self.world, self.rank, self.slot_rays, n, int(num_rays),
             float(fov), self.flags, stream_ptr), "rl_calc_range_fan_allgather")
+
+    def march_angles(self, marcher, poses: torch.Tensor, angles: torch.Tensor, stream_ptr: int,
+                     buf: Optional[int] = None):
+        """calc_range_repeat_angles of this rank's poses into slot ``rank`` of every GPU's next buffer set."""
+        n, na = poses.shape[0], angles.shape[0]
+        self._native.check(self._native.lib().rl_calc_range_repeat_angles_allgather(
+            marcher._h, poses.data_ptr(), angles.data_ptr(), self._take(buf), self.world, self.rank, self.slot_rays,
+            n, int(na), self.flags, stream_ptr), "rl_calc_range_repeat_angles_allgather")
 
     def sync(self):
         """Stream-ordered barrier: returns (on the stream) once every rank's march has completed."""
@@ -163,6 +196,15 @@ def gpu_march_fn(marcher, fov: float, num_rays: int) -> Callable:
     return run
 
 
+def gpu_march_angles_fn(marcher, angles: torch.Tensor) -> Callable:
+    """The product march of the particle-filter shape (BASELINE config 3):
+    ``PyRayMarchingGPU.calc_range_repeat_angles`` on device tensors; ``num_rays = len(angles)``."""
+    def run(poses: torch.Tensor, out: torch.Tensor):
+        if poses.shape[0]:
+            marcher.calc_range_repeat_angles(poses, angles, out)
+    return run
+
+
 class ShardedScanner:
     """``scan(poses)`` over the whole process group.
 
@@ -170,6 +212,10 @@ class ShardedScanner:
     returns: (N * num_rays,) float32 ranges, pose-major -- on every rank for ``gather="all"``, on
              ``root`` only (None elsewhere) for ``gather="root"``, and just the local shard
              (``hi - lo`` poses) for ``gather="none"``.
+    chunks:  ``gather="all"`` only: the rank's shard is marched in this many pieces and the all-gather of
+             piece k-1 (``async_op`` on the collective's own stream) overlaps the march of piece k
+             (SURVEY.md section 5).  The fused path (:meth:`scan_fused`) needs no such pipeline: its
+             stores travel while the march runs.
     """
 
     def __init__(self, march_fn: Callable, num_rays: int, device: torch.device,
@@ -181,6 +227,7 @@ class ShardedScanner:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.chunks = max(1, int(chunks))
+        self._peer = None
 
     def scan(self, poses: torch.Tensor, gather: str = "all", root: int = 0):
         if gather not in ("all", "root", "none"):
@@ -189,12 +236,27 @@ class ShardedScanner:
         lo, hi = shard_bounds(n, self.world, self.rank)
         per = -(-n // self.world) if n > 0 else 0
         R = self.num_rays
+        cnt = hi - lo
         # equal, padded shards: all_gather needs the same count from every rank
         local = torch.zeros(per * R, dtype=torch.float32, device=self.device)
         mine = poses[lo:hi].to(self.device).contiguous()
-        self.march_fn(mine, local[:(hi - lo) * R])
+        if gather == "all" and self.world > 1 and self.chunks > 1 and per > 0:
+            full = torch.empty(self.world * per * R, dtype=torch.float32, device=self.device)
+            C = min(self.chunks, per)
+            cuts = [per * i // C for i in range(C + 1)]   # in poses of the padded shard
+            pending = []
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                m0, m1 = min(a, cnt), min(b, cnt)
+                if m1 > m0:
+                    self.march_fn(mine[m0:m1], local[m0 * R:m1 * R])
+                outs = [full[r * per * R + a * R: r * per * R + b * R] for r in range(self.world)]
+                pending.append(dist.all_gather(outs, local[a * R:b * R], group=self.group, async_op=True))
+            for w in pending:
+                w.wait()
+            return full[:n * R]
+        self.march_fn(mine, local[:cnt * R])
         if gather == "none" or self.world == 1:
-            out = local[:(hi - lo) * R]
+            out = local[:cnt * R]
             return out if (gather != "root" or self.rank == root) else None
         if gather == "all":
             full = torch.empty(self.world * per * R, dtype=torch.float32, device=self.device)
@@ -206,22 +268,36 @@ class ShardedScanner:
             return None
         return torch.cat(parts)[:n * R]
 
-    def scan_fused(self, poses: torch.Tensor, marcher, fov: float, peer: "PeerGather" = None):
-        """All-gather fused into the march kernel (``rl_calc_range_fan_allgather``): every rank's ranges
-        are stored straight into every GPU's gathered buffer over NVLink while the march runs.
-        Returns the (N * num_rays,) gathered ranges (a view of the peer buffer, valid until the next
-        call) on every rank.  Pass a long-lived :class:`PeerGather` to avoid re-creating the mappings."""
+    def _peer_for(self, peer, need_rays):
+        if peer is not None:
+            return peer
+        if self._peer is None or self._peer.slot_rays < need_rays:
+            if self._peer is not None:
+                self._peer.close()
+            self._peer = PeerGather(self.device.index, max(need_rays, 1), self.group)
+        return self._peer
+
+    def scan_fused(self, poses: torch.Tensor, marcher, fov: float = 0.0, peer: "PeerGather" = None,
+                   angles: Optional[torch.Tensor] = None):
+        """All-gather fused into the march kernel (``rl_calc_range_fan_allgather``, or
+        ``rl_calc_range_repeat_angles_allgather`` when ``angles`` is given -- then ``num_rays`` must be
+        ``len(angles)``): every rank's ranges are stored straight into every GPU's gathered buffer over
+        NVLink while the march runs.  Returns the (N * num_rays,) gathered ranges on every rank: a view of
+        the peer buffer, valid until the call AFTER NEXT on any rank (see :class:`PeerGather`).  Pass a
+        long-lived :class:`PeerGather` to avoid re-creating the mappings."""
         n = poses.shape[0]
         lo, hi = shard_bounds(n, self.world, self.rank)
         per = -(-n // self.world) if n > 0 else 0
         R = self.num_rays
-        if peer is None:
-            peer = self._peer if getattr(self, "_peer", None) is not None and self._peer.slot_rays >= per * R else None
-            if peer is None:
-                peer = self._peer = PeerGather(self.device.index, max(per * R, 1), self.group)
+        if angles is not None and angles.shape[0] != R:
+            raise ValueError("scan_fused: len(angles) must equal num_rays")
+        peer = self._peer_for(peer, per * R)
         mine = poses[lo:hi].to(self.device).contiguous()
         stream = int(torch.cuda.current_stream(self.device.index).cuda_stream)
-        peer.march(marcher, mine, fov, R, stream)
+        if angles is None:
+            peer.march(marcher, mine, fov, R, stream)
+        else:
+            peer.march_angles(marcher, mine, angles, stream)
         peer.sync()
         full = peer.tensor()
         if peer.slot_rays == per * R:
@@ -229,6 +305,35 @@ class ShardedScanner:
         # slots padded beyond this batch's shard size: compact the used parts
         return torch.cat([full[r * peer.slot_rays: r * peer.slot_rays + max(0, min(n, (r + 1) * per) - r * per) * R]
                           for r in range(self.world)])
+
+    def scan_fused_chunks(self, poses: torch.Tensor, marcher, fov: float, chunk_poses: int,
+                          peer: "PeerGather" = None, angles: Optional[torch.Tensor] = None):
+        """Generator over a batch too large to gather into one buffer (BASELINE config 5: 17.3 GB of
+        ranges): the rank's shard is marched ``chunk_poses`` poses at a time, each piece all-gathered by the
+        fused kernel into the peer buffers (which alternate, so piece k+1 is marched while piece k is being
+        consumed) and yielded as ``(first_pose_in_shard, count_per_rank, gathered)`` with ``gathered`` the
+        (world, chunk_poses * num_rays) view: row r = ranges of rank r's poses
+        ``[r*per + first, r*per + first + count_r)``, where ``count_r`` is ``count_per_rank[r]``."""
+        n = poses.shape[0]
+        lo, hi = shard_bounds(n, self.world, self.rank)
+        per = -(-n // self.world) if n > 0 else 0
+        R = self.num_rays
+        chunk_poses = max(1, int(chunk_poses))
+        peer = self._peer_for(peer, chunk_poses * R)
+        mine = poses[lo:hi].to(self.device).contiguous()
+        stream = int(torch.cuda.current_stream(self.device.index).cuda_stream)
+        for first in range(0, per, chunk_poses):
+            a, b = min(first, hi - lo), min(first + chunk_poses, hi - lo)
+            if b > a:
+                if angles is None:
+                    peer.march(marcher, mine[a:b], fov, R, stream)
+                else:
+                    peer.march_angles(marcher, mine[a:b], angles, stream)
+            else:
+                peer._take(None)   # nothing of mine in this piece: still advance to the buffer set the others write
+            peer.sync()
+            counts = [max(0, min(first + chunk_poses, min(n, (r + 1) * per) - r * per) - first) for r in range(self.world)]
+            yield first, counts, peer.tensor().view(self.world, peer.slot_rays)
 
 
 def gpu_rollout_fn(car, marcher, fov: float, action_every: int = 10, dt: float = 0.01,

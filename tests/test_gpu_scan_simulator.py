@@ -121,5 +121,9 @@ def test_racecar_simulator_facade(orc, sim_env, colombia_scan):
     edge = orc.car_edge_distances(p, 1080, -4.71 / 2.0, 4.71 / 1080, 0.275)
     want_idx = orc.car_is_crashed(marcher.calc_range_fan(poses, 1080, 4.71), edge, 1080, 20, 0.001)
     assert rcs.checkCollisionMany(poses) == want_idx
+    # the reference's side effect on request: every range of the batch in output_vector_many
+    rcs.scan_simulator.output_vector_many[:] = -7.0
+    assert rcs.checkCollisionMany(poses, want_ranges=True) == want_idx
+    assert np.array_equal(rcs.scan_simulator.output_vector_many, marcher.calc_range_fan(poses, 1080, 4.71))
     rcs.stop()
     assert not rcs.getState().any()
