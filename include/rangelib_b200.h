@@ -101,6 +101,17 @@ RL_API int32_t rl_map_from_image(const uint8_t *pixels, int32_t width, int32_t h
                           double resolution, double origin_x, double origin_y, double origin_yaw,
                           int32_t device, rl_map **out);
 
+/* Colour / alpha images (launch/simulate.launch:8-9 hands map_server any image it can load): `channels`   */
+/* interleaved bytes per pixel (1 grey, 2 grey+alpha, 3 RGB, 4 RGBA).  map_server averages the channels of  */
+/* a pixel -- all of them in trinary mode or when the image has no alpha (`has_alpha` = 0), all but the      */
+/* last otherwise -- then applies the same rules to the average; in scale mode a pixel whose LAST byte is   */
+/* 0 and whose shade lies between the thresholds becomes unknown (ROS map_server image_loader.cpp).         */
+RL_API int32_t rl_map_from_image_channels(const uint8_t *pixels, int32_t width, int32_t height, int32_t channels,
+                                          int32_t has_alpha, int32_t negate, double occupied_thresh,
+                                          double free_thresh, int32_t mode, int32_t binarise, double resolution,
+                                          double origin_x, double origin_y, double origin_yaw, int32_t device,
+                                          rl_map **out);
+
 /* From OccupancyGrid.data (int8, row-major from the bottom-left cell, width = columns). */
 RL_API int32_t rl_map_from_occupancy(const int8_t *data, int32_t width, int32_t height, int32_t binarise,
                               double resolution, double origin_x, double origin_y,
@@ -185,6 +196,9 @@ RL_API int32_t rl_peer_free(int32_t device, void *d_ptr);
 /* starts storing into every GPU's buffer at once, so either barrier before the call as well or     */
 /* alternate between two sets of buffers (pyracecarsimulator_b200.sharded.PeerGather does the latter). */
 #define RL_GATHER_MULTICAST 1u
+/* with RL_GATHER_MULTICAST: multimem.st.weak instead of .relaxed.sys (the kernel boundary and the barrier that */
+/* follows publish the stores either way)                                                                   */
+#define RL_GATHER_WEAK 2u
 RL_API int32_t rl_calc_range_fan_allgather(rl_marcher *m, const float *d_poses, int64_t pose_stride_rows,
                                            void *const *peer_bufs, int32_t world, int32_t rank,
                                            int64_t slot_rays, int64_t num_poses, int32_t num_rays,

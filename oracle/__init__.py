@@ -71,6 +71,8 @@ def lib():
     L = C.CDLL(build())
     L.orc_mapserver_occupancy.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, i8p]
     L.orc_mapserver_occupancy_mode.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, i8p]
+    L.orc_mapserver_occupancy_channels.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                                   C.c_double, C.c_int, i8p]
     L.orc_omap_from_grid.argtypes = [i8p, C.c_int64, C.c_int, u8p]
     L.orc_edt_float.argtypes = [u8p, C.c_int, C.c_int, f32p, C.c_void_p]
     L.orc_edt_exact.argtypes = [u8p, C.c_int, C.c_int, i32p]
@@ -119,6 +121,16 @@ def mapserver_occupancy(img, negate=0, occupied_thresh=0.65, free_thresh=0.196, 
     else:
         lib().orc_mapserver_occupancy_mode(img, w, h, int(negate), float(occupied_thresh), float(free_thresh),
                                            MODES[mode], out)
+    return out
+
+
+def mapserver_occupancy_channels(img, has_alpha, negate=0, occupied_thresh=0.65, free_thresh=0.196, mode="trinary"):
+    """(H, W, C) uint8 colour / alpha image -> (H, W) int8 OccupancyGrid (map_server's channel averaging)."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w, c = img.shape
+    out = np.empty((h, w), dtype=np.int8)
+    lib().orc_mapserver_occupancy_channels(img.ctypes.data, w, h, c, int(bool(has_alpha)), int(negate),
+                                           float(occupied_thresh), float(free_thresh), MODES[mode], out)
     return out
 
 

@@ -53,7 +53,7 @@
 /* ------------------------------------------------------------------------- */
 static int8_t mapserver_cell(int p, int negate, double occupied_thresh, double free_thresh, int mode)
 {
-    if (mode == 2) return (int8_t)(unsigned char)p;            /* raw: the pixel value itself */
+    if (mode == 2) return (int8_t)(unsigned char)(negate ? 255 - p : p);   /* raw: the (negated) pixel value itself */
     double shade = negate ? p / 255.0 : (255 - p) / 255.0;
     if (shade > occupied_thresh) return 100;
     if (shade < free_thresh) return 0;
@@ -70,6 +70,36 @@ ORC_EXPORT void orc_mapserver_occupancy_mode(const uint8_t *img, int img_w, int 
         int8_t *dst = grid + (size_t)(img_h - 1 - j) * img_w;
         const uint8_t *src = img + (size_t)j * img_w;
         for (int i = 0; i < img_w; ++i) dst[i] = mapserver_cell(src[i], negate, occupied_thresh, free_thresh, mode);
+    }
+}
+
+/* Colour / alpha images: ROS1 map_server image_loader.cpp (third-party, not in the reference checkout;   */
+/* launch/simulate.launch:8-9 hands it whatever image the yaml names).  Per pixel of `channels` bytes:    */
+/*   avg_channels = (mode == trinary || !has_alpha) ? channels : channels - 1;                            */
+/*   color_avg = sum(first avg_channels bytes) / (double)avg_channels;  alpha = channels == 1 ? 1 : last  */
+/*   byte;  negate -> 255 - color_avg;  raw: value = color_avg;  else occ = (255 - color_avg) / 255 and   */
+/*   > occupied_thresh -> 100, < free_thresh -> 0, trinary or alpha < 1 -> -1, else 1 + 98 * ratio.       */
+ORC_EXPORT void orc_mapserver_occupancy_channels(const uint8_t *img, int img_w, int img_h, int channels,
+                                                 int has_alpha, int negate, double occupied_thresh,
+                                                 double free_thresh, int mode, int8_t *grid)
+{
+    const int avg = (mode == 0 || !has_alpha) ? channels : channels - 1;
+    for (int j = 0; j < img_h; ++j) {
+        int8_t *dst = grid + (size_t)(img_h - 1 - j) * img_w;
+        for (int i = 0; i < img_w; ++i) {
+            const uint8_t *p = img + ((size_t)j * img_w + i) * channels;
+            int sum = 0;
+            for (int k = 0; k < avg; ++k) sum += p[k];
+            double color_avg = sum / (double)avg;
+            const double alpha = channels == 1 ? 1.0 : (double)p[channels - 1];
+            if (negate) color_avg = 255 - color_avg;
+            if (mode == 2) { dst[i] = (int8_t)(unsigned char)color_avg; continue; }
+            const double occ = (255 - color_avg) / 255.0;
+            if (occ > occupied_thresh) dst[i] = 100;
+            else if (occ < free_thresh) dst[i] = 0;
+            else if (mode == 0 || alpha < 1.0) dst[i] = -1;
+            else dst[i] = (int8_t)(unsigned char)(1 + 98 * ((occ - free_thresh) / (occupied_thresh - free_thresh)));
+        }
     }
 }
 

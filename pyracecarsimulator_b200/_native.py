@@ -42,6 +42,7 @@ SIGNATURES = {
     "rl_last_error": (C.c_char_p, []),
     "rl_device_count": (_i32, [C.POINTER(_i32)]),
     "rl_map_from_image": (_i32, [_vp, _i32, _i32, _i32, _d, _d, _i32, _i32, _d, _d, _d, _d, _i32, C.POINTER(_vp)]),
+    "rl_map_from_image_channels": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _d, _d, _i32, _i32, _d, _d, _d, _d, _i32, C.POINTER(_vp)]),
     "rl_map_from_occupancy": (_i32, [_vp, _i32, _i32, _i32, _d, _d, _d, _d, _i32, C.POINTER(_vp)]),
     "rl_map_from_cells": (_i32, [_vp, _i32, _i32, _d, _d, _d, _d, _i32, C.POINTER(_vp)]),
     "rl_map_shape": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),

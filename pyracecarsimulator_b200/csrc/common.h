@@ -45,9 +45,22 @@ struct WorldFrame {
     float scale, angle, origin_x, origin_y, sin_angle, cos_angle, inv_scale, rotation_const;
 };
 
+// The march field: what a ray adds to its parameter t after sampling a cell.  The reference's loop is
+//     d = dist[cell]; if (d <= 0) hit; t += max(0.999 * d, 1); if (!(t < max_range)) miss;
+// max(0.999 * d, 1) is a pure function of the cell, so the ingest evaluates it once per cell (the same two
+// fp32 operations, same bits) and stores +inf for occupied cells (d == 0): then t + step = inf fails the one
+// remaining test `t < max_range` and which exit it was is decided once, after the loop.  Three instructions
+// fewer per march step (FMUL, FMNMX, FSETP) in an issue-bound loop; results are bit-identical.
+#ifdef __CUDACC__
+__device__ __forceinline__ float march_step_of(float d)
+{
+    return d <= 0.0f ? __int_as_float(0x7f800000) : fmaxf(__fmul_rn(d, 0.999f), 1.0f);
+}
+#endif
+
 // Passed by value to every march kernel.
 struct MarchParams {
-    const float *dist;  // dist[row * cols + col], fp32 pixels
+    const float *dist;  // the march field step[row * cols + col] (see march_step_of), fp32 pixels
     int rows, cols;     // rows = OMap.width (msg.info.height), cols = OMap.height (msg.info.width)
     float frows, fcols;
     float max_range;    // pixels
@@ -63,6 +76,7 @@ struct rl_map {
     uint8_t *d_occ = nullptr;   // rows*cols, 0/1
     int32_t *d_dist2 = nullptr; // rows*cols exact squared distance
     float *d_dist = nullptr;    // rows*cols sqrt
+    float *d_step = nullptr;    // rows*cols march field derived from d_dist (rl::march_step_of): what the kernels read
     float ingest_ms = 0.f;
     std::atomic<int> refs{1};
 };

@@ -63,6 +63,36 @@ edt_classify_kernel(const uint8_t *__restrict__ src, int rows, int cols, int fli
     seg_last[(size_t)seg * cols + c] = last;
 }
 
+// The same for colour / alpha images (map_server averages the channels of a pixel before thresholding,
+// ROS map_server image_loader.cpp): `channels` bytes per pixel, the first `avg` of them summed; every
+// rule downstream is a function of that sum (0 .. 255*avg) and of "last byte == 0" (map_server's alpha
+// test, which in scale mode turns an in-between cell into unknown), so two bit LUTs over the sum.
+struct SumLut { uint32_t w[2][32]; };       // [last byte == 0][bit = sum]
+
+__global__ void __launch_bounds__(128)
+edt_classify_multi_kernel(const uint8_t *__restrict__ src, int rows, int cols, int channels, int avg, int flip,
+                          SumLut lut, uint8_t *__restrict__ occ, int *__restrict__ seg_first,
+                          int *__restrict__ seg_last)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int seg = blockIdx.y;
+    if (c >= cols) return;
+    const int r0 = seg * SEG_ROWS, r1 = min(rows, r0 + SEG_ROWS);
+    int first = SEG_NONE_FIRST, last = SEG_NONE_LAST;
+    for (int r = r0; r < r1; ++r) {
+        const int sr = flip ? rows - 1 - r : r;
+        const uint8_t *px = src + ((size_t)sr * cols + c) * channels;
+        uint32_t sum = 0;
+        for (int k = 0; k < avg; ++k) sum += px[k];
+        const int a0 = channels > 1 && px[channels - 1] == 0;
+        const uint32_t o = (lut.w[a0][sum >> 5] >> (sum & 31u)) & 1u;
+        occ[(size_t)r * cols + c] = (uint8_t)o;
+        if (o) { first = min(first, r); last = r; }
+    }
+    seg_first[(size_t)seg * cols + c] = first;
+    seg_last[(size_t)seg * cols + c] = last;
+}
+
 // Column pass, step 2 (one thread per column, in place): seg_last[seg] becomes the last occupied row ABOVE
 // the segment (in any earlier segment), seg_first[seg] the first occupied row BELOW it.  The loads do not
 // depend on each other, so the 2 * nseg of them pipeline; searching the neighbouring segments from inside
@@ -72,19 +102,29 @@ edt_seg_scan_kernel(int cols, int nseg, int *__restrict__ seg_first, int *__rest
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cols) return;
+    // batches of 16 loads that do not depend on each other, then the 16 dependent selects + stores
+    constexpr int NB = 16;
     int carry = SEG_NONE_LAST;
-#pragma unroll 8
-    for (int s2 = 0; s2 < nseg; ++s2) {
-        const int l = seg_last[(size_t)s2 * cols + c];
-        seg_last[(size_t)s2 * cols + c] = carry;
-        if (l != SEG_NONE_LAST) carry = l;
+    for (int s0 = 0; s0 < nseg; s0 += NB) {
+        int v[NB];
+#pragma unroll
+        for (int u = 0; u < NB; ++u) v[u] = (s0 + u < nseg) ? seg_last[(size_t)(s0 + u) * cols + c] : SEG_NONE_LAST;
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            if (s0 + u < nseg) seg_last[(size_t)(s0 + u) * cols + c] = carry;
+            if (v[u] != SEG_NONE_LAST) carry = v[u];
+        }
     }
     carry = SEG_NONE_FIRST;
-#pragma unroll 8
-    for (int s2 = nseg - 1; s2 >= 0; --s2) {
-        const int f = seg_first[(size_t)s2 * cols + c];
-        seg_first[(size_t)s2 * cols + c] = carry;
-        if (f != SEG_NONE_FIRST) carry = f;
+    for (int s0 = nseg - 1; s0 >= 0; s0 -= NB) {
+        int v[NB];
+#pragma unroll
+        for (int u = 0; u < NB; ++u) v[u] = (s0 - u >= 0) ? seg_first[(size_t)(s0 - u) * cols + c] : SEG_NONE_FIRST;
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            if (s0 - u >= 0) seg_first[(size_t)(s0 - u) * cols + c] = carry;
+            if (v[u] != SEG_NONE_FIRST) carry = v[u];
+        }
     }
 }
 
@@ -139,7 +179,7 @@ edt_cols_kernel(const uint8_t *__restrict__ occ, int rows, int cols, int nseg,
 // bisection order do not pile onto one bank.
 constexpr uint32_t G2_FAR = 0x3fffffffu;
 constexpr int ROW_THREADS = 256;
-constexpr int SCAN_BUDGET = 32;
+constexpr int SCAN_BUDGET = 128;   // indoor-style maps (synth 2049^2: 64..128 per cell) stay on the scan
 constexpr int ROWS_AUTO = 0, ROWS_SCAN = 1, ROWS_DC = 2;
 
 __device__ __forceinline__ int sw(int i) { return i + (i >> 5); }
@@ -155,7 +195,7 @@ __device__ __forceinline__ void dc_bounds(const uint16_t *opt, int cols, int j, 
 
 __global__ void __launch_bounds__(ROW_THREADS)
 edt_rows_kernel(const uint16_t *__restrict__ g, int rows, int cols, int log2T, int force, int budget,
-                int32_t *__restrict__ dist2, float *__restrict__ dist)
+                int32_t *__restrict__ dist2, float *__restrict__ dist, float *__restrict__ step)
 {
     extern __shared__ uint32_t g2[];                                     // sw(cols) words of g^2 ...
     uint16_t *opt = reinterpret_cast<uint16_t *>(g2 + sw(cols) + 1);     // ... then sw(cols) argmins
@@ -183,6 +223,7 @@ edt_rows_kernel(const uint16_t *__restrict__ g, int rows, int cols, int log2T, i
             const size_t o = (size_t)r * cols + q;
             dist2[o] = RL_DIST2_INF;
             dist[o] = sqrtf(1e20f);   // what the reference's INF = 1e20 transform leaves on an empty map
+            step[o] = rl::march_step_of(sqrtf(1e20f));
         }
         return;
     }
@@ -212,29 +253,62 @@ edt_rows_kernel(const uint16_t *__restrict__ g, int rows, int cols, int log2T, i
             if (best >= G2_FAR) {
                 dist2[o] = RL_DIST2_INF;
                 dist[o] = sqrtf(1e20f);
+                step[o] = rl::march_step_of(sqrtf(1e20f));
             } else {
                 dist2[o] = (int32_t)best;
                 dist[o] = sqrtf((float)best);
+                step[o] = rl::march_step_of(sqrtf((float)best));
             }
         }
         return;
     }
     for (int h = 1 << (log2T - 1); h >= 1; h >>= 1) {
         const int nq = (cols / h + 1) >> 1;   // queries of this level: (2j+1) h <= cols
-        if (nq >= ROW_THREADS) {              // a query per thread, several per thread at the bottom levels
-            for (int j = tid; j < nq; j += ROW_THREADS) {
-                int q, lo, hi;
-                dc_bounds(opt, cols, j, h, q, lo, hi);
+        if (nq > ROW_THREADS / 32) {          // a query per thread (several per thread at the bottom levels)
+            for (int base = 0; base < nq; base += ROW_THREADS) {
+                // consecutive queries go to different warps, so the few long ranges of a level spread over the CTA
+                const int j = base + (tid & 31) * (ROW_THREADS / 32) + (tid >> 5);
+                const bool active = j < nq;
+                int q = 0, lo = 0, hi = -1;
+                if (active) dc_bounds(opt, cols, j, h, q, lo, hi);
                 uint32_t bv = 0xffffffffu;
                 int bk = lo;
-                for (int k = lo; k <= hi; ++k) {
-                    const int d = q - k;
-                    const uint32_t v = (uint32_t)(d * d) + g2[sw(k)];
-                    if (v < bv) { bv = v; bk = k; }
+                // The ranges of a level sum to <= W + nq, but one query may own most of that (on a sparse row
+                // the leftmost query of every level searches [0, argmin of its right neighbour]): ranges longer
+                // than LONG are searched by the whole warp, one after the other, the short ones by their lane.
+                constexpr int LONG = 24;
+                const bool is_long = active && hi - lo >= LONG;
+                if (active && !is_long) {
+                    for (int k = lo; k <= hi; ++k) {
+                        const int d = q - k;
+                        const uint32_t v = (uint32_t)(d * d) + g2[sw(k)];
+                        if (v < bv) { bv = v; bk = k; }
+                    }
                 }
-                opt[sw(q)] = (uint16_t)bk;
+                unsigned todo = __ballot_sync(0xffffffffu, is_long);
+                const int lane = tid & 31;
+                while (todo) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int qs = __shfl_sync(0xffffffffu, q, src), los = __shfl_sync(0xffffffffu, lo, src),
+                              his = __shfl_sync(0xffffffffu, hi, src);
+                    uint32_t cv = 0xffffffffu;
+                    int ck = los;
+                    for (int k = los + lane; k <= his; k += 32) {
+                        const int d = qs - k;
+                        const uint32_t v = (uint32_t)(d * d) + g2[sw(k)];
+                        if (v < cv) { cv = v; ck = k; }
+                    }
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const uint32_t v2 = __shfl_xor_sync(0xffffffffu, cv, o);
+                        const int k2 = __shfl_xor_sync(0xffffffffu, ck, o);
+                        if (v2 < cv) { cv = v2; ck = k2; }
+                    }
+                    if (lane == src) { bv = cv; bk = ck; }
+                }
+                if (active) opt[sw(q)] = (uint16_t)bk;
             }
-        } else if (nq > 0) {                  // a group of G threads per query
+        } else if (nq > 0) {                  // top levels, at most 8 queries: a group of G >= 32 threads per query
             const int G = 1 << (31 - __clz(ROW_THREADS / nq));
             const int grp = tid / G, l = tid & (G - 1);
             const bool active = grp < nq;
@@ -278,9 +352,11 @@ edt_rows_kernel(const uint16_t *__restrict__ g, int rows, int cols, int log2T, i
         if (best >= G2_FAR) {
             dist2[o] = RL_DIST2_INF;
             dist[o] = sqrtf(1e20f);
+            step[o] = rl::march_step_of(sqrtf(1e20f));
         } else {
             dist2[o] = (int32_t)best;
             dist[o] = sqrtf((float)best);
+            step[o] = rl::march_step_of(sqrtf((float)best));
         }
     }
 }
@@ -301,7 +377,8 @@ rl::WorldFrame make_world(double resolution, double ox, double oy, double yaw)
 }
 
 int32_t build_map(const uint8_t *src, int width, int height, int flip, const ByteLut &lut,
-                  double resolution, double ox, double oy, double yaw, int device, rl_map **out)
+                  double resolution, double ox, double oy, double yaw, int device, rl_map **out,
+                  int channels = 1, int avg = 1, const SumLut *sum_lut = nullptr)
 {
     if (!src || !out) return rl::fail(RL_ERR_BAD_ARG, "map ingest: null pointer");
     if (width <= 0 || height <= 0 || width > MAX_SIDE || height > MAX_SIDE)
@@ -332,7 +409,7 @@ int32_t build_map(const uint8_t *src, int width, int height, int flip, const Byt
         cudaFree(d_seg);
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
-        if (all) { cudaFree(m->d_occ); cudaFree(m->d_dist2); cudaFree(m->d_dist); delete m; }
+        if (all) { cudaFree(m->d_occ); cudaFree(m->d_dist2); cudaFree(m->d_dist); cudaFree(m->d_step); delete m; }
     };
 #define RL_TRY(expr)                                                                           \
     do {                                                                                       \
@@ -343,13 +420,14 @@ int32_t build_map(const uint8_t *src, int width, int height, int flip, const Byt
                             std::string(#expr) + ": " + cudaGetErrorString(_e));               \
         }                                                                                      \
     } while (0)
-    RL_TRY(cudaMalloc(&d_src, n));
+    RL_TRY(cudaMalloc(&d_src, n * channels));
     RL_TRY(cudaMalloc(&d_g, n * sizeof(uint16_t)));
     RL_TRY(cudaMalloc(&d_seg, (size_t)2 * nseg * width * sizeof(int)));
     RL_TRY(cudaMalloc(&m->d_occ, n));
     RL_TRY(cudaMalloc(&m->d_dist2, n * sizeof(int32_t)));
     RL_TRY(cudaMalloc(&m->d_dist, n * sizeof(float)));
-    RL_TRY(cudaMemcpy(d_src, src, n, cudaMemcpyHostToDevice));
+    RL_TRY(cudaMalloc(&m->d_step, n * sizeof(float)));
+    RL_TRY(cudaMemcpy(d_src, src, n * channels, cudaMemcpyHostToDevice));
     RL_TRY(cudaEventCreate(&e0));
     RL_TRY(cudaEventCreate(&e1));
     const size_t padded = (size_t)width + ((size_t)width >> 5) + 2;
@@ -364,14 +442,15 @@ int32_t build_map(const uint8_t *src, int width, int height, int flip, const Byt
     {
         const dim3 grid((width + 127) / 128, nseg);
         int *seg_first = d_seg, *seg_last = d_seg + (size_t)nseg * width;
-        edt_classify_kernel<<<grid, 128>>>(d_src, height, width, flip, lut, m->d_occ, seg_first, seg_last);
+        if (sum_lut) edt_classify_multi_kernel<<<grid, 128>>>(d_src, height, width, channels, avg, flip, *sum_lut, m->d_occ, seg_first, seg_last);
+        else edt_classify_kernel<<<grid, 128>>>(d_src, height, width, flip, lut, m->d_occ, seg_first, seg_last);
         edt_seg_scan_kernel<<<(width + 127) / 128, 128>>>(width, nseg, seg_first, seg_last);
         edt_cols_kernel<<<grid, 128>>>(m->d_occ, height, width, nseg, seg_first, seg_last, d_g);
     }
     {
         int log2T = 1;
         while ((1 << log2T) < width + 1) ++log2T;
-        edt_rows_kernel<<<height, ROW_THREADS, smem>>>(d_g, height, width, log2T, force, budget, m->d_dist2, m->d_dist);
+        edt_rows_kernel<<<height, ROW_THREADS, smem>>>(d_g, height, width, log2T, force, budget, m->d_dist2, m->d_dist, m->d_step);
     }
     RL_TRY(cudaGetLastError());
     RL_TRY(cudaEventRecord(e1, 0));
@@ -395,6 +474,7 @@ void rl_map_release(const rl_map *cm)
         cudaFree(m->d_occ);
         cudaFree(m->d_dist2);
         cudaFree(m->d_dist);
+        cudaFree(m->d_step);
         delete m;
     }
 }
@@ -412,7 +492,7 @@ int32_t rl_map_from_image(const uint8_t *pixels, int32_t width, int32_t height, 
     ByteLut lut{};
     for (int p = 0; p < 256; ++p) {
         int v;
-        if (mode == RL_MAP_RAW) v = (int8_t)(unsigned char)p;
+        if (mode == RL_MAP_RAW) v = (int8_t)(unsigned char)(negate ? 255 - p : p);   // map_server negates before the raw copy
         else {
             double shade = negate ? p / 255.0 : (255 - p) / 255.0;
             if (shade > occupied_thresh) v = 100;
@@ -425,6 +505,37 @@ int32_t rl_map_from_image(const uint8_t *pixels, int32_t width, int32_t height, 
     }
     return build_map(pixels, width, height, /*flip=*/1, lut, resolution, origin_x, origin_y,
                      origin_yaw, device, out);
+}
+
+int32_t rl_map_from_image_channels(const uint8_t *pixels, int32_t width, int32_t height, int32_t channels,
+                                   int32_t has_alpha, int32_t negate, double occupied_thresh, double free_thresh,
+                                   int32_t mode, int32_t binarise, double resolution, double origin_x,
+                                   double origin_y, double origin_yaw, int32_t device, rl_map **out)
+{
+    if (mode < RL_MAP_TRINARY || mode > RL_MAP_RAW) return rl::fail(RL_ERR_BAD_ARG, "rl_map_from_image_channels: unknown mode");
+    if (channels < 1 || channels > 4) return rl::fail(RL_ERR_BAD_ARG, "rl_map_from_image_channels: 1 to 4 channels");
+    // map_server: trinary mode averages every channel (alpha included), the other modes leave a real alpha out
+    const int avg = (mode == RL_MAP_TRINARY || !has_alpha) ? channels : channels - 1;
+    SumLut lut{};
+    for (int a0 = 0; a0 < 2; ++a0) {
+        for (int sum = 0; sum <= 255 * avg; ++sum) {
+            double color_avg = sum / (double)avg;
+            if (negate) color_avg = 255 - color_avg;
+            int v;
+            if (mode == RL_MAP_RAW) v = (int8_t)(unsigned char)color_avg;
+            else {
+                const double shade = (255 - color_avg) / 255.0;
+                if (shade > occupied_thresh) v = 100;
+                else if (shade < free_thresh) v = 0;
+                else if (mode == RL_MAP_TRINARY || (channels > 1 && a0)) v = -1;
+                else v = (int8_t)(unsigned char)(1 + 98 * ((shade - free_thresh) / (occupied_thresh - free_thresh)));
+            }
+            if (binarise) v = (v > 0) ? 255 : 0;
+            if (v > 10) lut.w[a0][sum >> 5] |= 1u << (sum & 31);
+        }
+    }
+    return build_map(pixels, width, height, /*flip=*/1, ByteLut{}, resolution, origin_x, origin_y, origin_yaw,
+                     device, out, channels, avg, &lut);
 }
 
 int32_t rl_map_from_occupancy(const int8_t *data, int32_t width, int32_t height, int32_t binarise,

@@ -76,7 +76,9 @@ struct PeerOut {
 
 __device__ __forceinline__ void peer_store(const PeerOut &peers, int64_t i, float r)
 {
-    if (peers.multicast) {   // the NVSwitch replicates the store to all GPUs of the multicast group
+    if (peers.multicast == 2) {   // RL_GATHER_WEAK: no ordering asked of the store; the kernel boundary + barrier publish it
+        asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(peers.buf[0] + peers.offset + i), "f"(r) : "memory");
+    } else if (peers.multicast) {   // the NVSwitch replicates the store to all GPUs of the multicast group
         asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(peers.buf[0] + peers.offset + i), "f"(r)
                      : "memory");
     } else {
@@ -87,7 +89,11 @@ __device__ __forceinline__ void peer_store(const PeerOut &peers, int64_t i, floa
 
 __device__ __forceinline__ void peer_store4(const PeerOut &peers, int64_t i, float4 v)
 {
-    if (peers.multicast) {
+    if (peers.multicast == 2) {
+        asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(peers.buf[0] + peers.offset + i),
+                     "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                     : "memory");
+    } else if (peers.multicast) {
         asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(peers.buf[0] + peers.offset + i),
                      "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                      : "memory");
@@ -360,7 +366,7 @@ int32_t fill_peers(PeerOut &po, void *const *peer_bufs, int32_t world, int32_t r
         po.buf[q] = static_cast<float *>(peer_bufs[q]);
     }
     po.world = world;
-    po.multicast = (flags & RL_GATHER_MULTICAST) ? 1 : 0;
+    po.multicast = (flags & RL_GATHER_MULTICAST) ? ((flags & RL_GATHER_WEAK) ? 2 : 1) : 0;
     po.offset = (int64_t)rank * slot_rays;
     return RL_OK;
 }
@@ -390,7 +396,7 @@ int32_t rl_marcher_create(const rl_map *map, float max_range_px, uint32_t flags,
     rl_map_retain(map);
     m->map = map;
     m->flags = flags;
-    m->P.dist = map->d_dist;
+    m->P.dist = map->d_step;
     m->P.rows = map->rows;
     m->P.cols = map->cols;
     m->P.frows = (float)map->rows;

@@ -34,8 +34,8 @@ __device__ __forceinline__ GridPose world_to_grid(const WorldFrame &w, float xw,
 // (profiles/r01_timeline.md).  After TAIL_AFTER plain steps a ray therefore also loads the cell
 // TAIL_AHEAD px further along itself at every step, into a ring of four registers that are only read
 // four steps later, so the touch never stalls the warp and the real sample finds its sector in L1.
-// The touched values never influence the result (the final test on them cannot be true: distances
-// are >= 0); measured 92.3 -> 86.5 us on BASELINE config 2.
+// The touched values never influence the result (the final test on them cannot be true: field values
+// are >= 1); measured 92.3 -> 86.5 us on BASELINE config 2.
 constexpr int TAIL_AFTER = 32;
 constexpr int TAIL_AHEAD = 12;
 
@@ -43,7 +43,7 @@ constexpr int TAIL_AHEAD = 12;
 // before the heading's sin/cos are evaluated and its latency hides behind that arithmetic.
 struct FirstSample {
     int px, py;
-    float d;     // valid when inside
+    float s;     // march field of the cell (valid when inside): +inf = occupied, else max(0.999 d, 1)
     bool inside;
 };
 
@@ -53,36 +53,39 @@ __device__ __forceinline__ FirstSample first_sample(const MarchParams &P, float 
     f.px = __float2int_rz(x0);   // fmaf(dx, 0, x0) == x0 for every finite dx
     f.py = __float2int_rz(y0);
     f.inside = (x0 == x0) && (y0 == y0) && (unsigned)f.px < (unsigned)P.rows && (unsigned)f.py < (unsigned)P.cols;
-    f.d = f.inside ? __ldg(P.dist + (f.px * P.cols + f.py)) : 0.0f;
+    f.s = f.inside ? __ldg(P.dist + (f.px * P.cols + f.py)) : 0.0f;
     return f;
 }
 
+// P.dist is the MARCH FIELD (common.h: march_step_of): s = +inf on an occupied cell, max(0.999 d, 1)
+// elsewhere -- exactly the value the reference's loop adds to t after sampling the cell, computed once
+// per cell by the ingest with the same two fp32 operations.  A hit therefore shows up as t + inf failing
+// `t < max_range`: one exit test per step, and which exit it was is decided once, after the loop.
 template <bool COUNT>
 __device__ __forceinline__ float march_ray(const MarchParams &P, float x0, float y0, float dx,
                                            float dy, uint32_t &steps, const FirstSample &f0)
 {
+    const float HIT = __int_as_float(0x7f800000);
     if (!f0.inside || !(dx == dx) || !(dy == dy)) return P.max_range;   // NaN pose/heading or pose outside the map
     if (COUNT) ++steps;
-    if (f0.d <= 0.0f) {   // pose inside an occupied cell: distance to that cell's corner
+    if (f0.s == HIT) {   // pose inside an occupied cell: distance to that cell's corner
         const float xd = __fsub_rn((float)f0.px, x0);
         const float yd = __fsub_rn((float)f0.py, y0);
         return sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
     }
-    float t = fmaxf(__fmul_rn(f0.d, 0.999f), 1.0f);   // 0 + step
+    float t = f0.s;   // 0 + step
     if (!(t < P.max_range)) return P.max_range;
-    // One exit branch per step: t is advanced before the hit test (harmless: a hit ends the ray) and
-    // which of the two exits it was is decided once, after the loop.
     int px, py, it = 1;
-    float d;
+    float s;
     bool tail = false;
     for (;;) {
         px = __float2int_rz(fmaf(dx, t, x0));
         py = __float2int_rz(fmaf(dy, t, y0));
-        if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) return P.max_range;
-        d = __ldg(P.dist + (px * P.cols + py));
+        if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) { s = 0.0f; break; }   // left the map: a miss
+        s = __ldg(P.dist + (px * P.cols + py));
         if (COUNT) ++steps;
-        t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
-        if (d <= 0.0f || !(t < P.max_range)) break;
+        t = __fadd_rn(t, s);
+        if (!(t < P.max_range)) break;
         if (++it == TAIL_AFTER) { tail = true; break; }
     }
     if (tail) {
@@ -95,21 +98,22 @@ __device__ __forceinline__ float march_ray(const MarchParams &P, float x0, float
             px = __float2int_rz(fx);                                                               \
             py = __float2int_rz(fy);                                                               \
             if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) { inside = false; break; } \
-            d = __ldg(P.dist + (px * P.cols + py));                                                \
+            s = __ldg(P.dist + (px * P.cols + py));                                                \
             if (COUNT) ++steps;                                                                    \
             const int ax = __float2int_rz(__fadd_rn(fx, adx)), ay = __float2int_rz(__fadd_rn(fy, ady)); \
             keep = __fadd_rn(keep, J);                                                             \
             if ((unsigned)ax < (unsigned)P.rows && (unsigned)ay < (unsigned)P.cols)                \
                 asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(J) : "l"(P.dist + (ax * P.cols + ay))); \
-            t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));                                   \
-            if (d <= 0.0f || !(t < P.max_range)) break;                                            \
+            t = __fadd_rn(t, s);                                                                   \
+            if (!(t < P.max_range)) break;                                                         \
         }
         for (;;) { RL_TAIL_STEP(j0) RL_TAIL_STEP(j1) RL_TAIL_STEP(j2) RL_TAIL_STEP(j3) }
 #undef RL_TAIL_STEP
-        if (__fadd_rn(__fadd_rn(keep, j0), __fadd_rn(j1, __fadd_rn(j2, j3))) < 0.0f) return -1.0f;  // never true
+        // the touched values (>= 1 or +inf) never influence the result; the test only keeps the loads alive
+        if (__fadd_rn(__fadd_rn(keep, j0), __fadd_rn(j1, __fadd_rn(j2, j3))) < 0.0f) return -1.0f;
         if (!inside) return P.max_range;
     }
-    if (d <= 0.0f) {
+    if (s == HIT) {
         const float xd = __fsub_rn((float)px, x0);
         const float yd = __fsub_rn((float)py, y0);
         return sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));

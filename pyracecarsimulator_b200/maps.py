@@ -70,36 +70,147 @@ def quaternion_to_yaw(q) -> float:
 
 
 # --------------------------------------------------------------------------- files
-def read_pgm(path: str) -> np.ndarray:
-    """Read a binary (P5) or ASCII (P2) 8-bit PGM -> (H, W) uint8, rows top to bottom.
-    maps/colombia/map.pgm is P2 with a ``#`` comment line."""
-    with open(path, "rb") as f:
-        raw = f.read()
-    magic = raw[:2]
-    if magic not in (b"P2", b"P5"):
-        raise ValueError(f"{path}: not a PGM (magic {magic!r})")
-    # header: magic, width, height, maxval separated by whitespace, '#' comments to end of line
+def _pnm_header(raw: bytes, path: str, count: int):
+    """Values after the magic number of a PNM file: whitespace separated, '#' comments to end of line."""
     pos, vals = 2, []
-    while len(vals) < 3:
+    while len(vals) < count:
         m = re.compile(rb"\s*(#[^\n]*\n|\d+)").match(raw, pos)
         if m is None:
-            raise ValueError(f"{path}: malformed PGM header")
+            raise ValueError(f"{path}: malformed PNM header")
         pos = m.end()
         if not m.group(1).startswith(b"#"):
             vals.append(int(m.group(1)))
-    w, h, maxval = vals
-    if maxval > 255:
-        raise ValueError(f"{path}: 16-bit PGM not supported")
-    if magic == b"P5":
+    return vals, pos
+
+
+def _narrow(samples: np.ndarray, maxval: int) -> np.ndarray:
+    """Samples with an arbitrary maxval -> 8 bits.  SDL_image (ROS1 map_server) rescales maxval < 255 as
+    v*255/maxval and refuses maxval > 255; deeper files are narrowed the same way here (rounded), which is
+    what an 8-bit export of the same picture would hold."""
+    if maxval == 255:
+        return samples.astype(np.uint8)
+    if maxval < 255:
+        return (samples.astype(np.int64) * 255 // maxval).astype(np.uint8)
+    return ((samples.astype(np.int64) * 255 + maxval // 2) // maxval).astype(np.uint8)
+
+
+def read_pnm(path: str) -> np.ndarray:
+    """PGM (P2 ASCII / P5 binary) or PPM (P3 / P6), any maxval up to 65535 -> (H, W) or (H, W, 3) uint8,
+    rows top to bottom.  maps/colombia/map.pgm is P2 with a ``#`` comment line."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    magic = raw[:2]
+    if magic not in (b"P2", b"P5", b"P3", b"P6"):
+        raise ValueError(f"{path}: not a PGM/PPM (magic {magic!r})")
+    (w, h, maxval), pos = _pnm_header(raw, path, 3)
+    if not 0 < maxval < 65536:
+        raise ValueError(f"{path}: bad maxval {maxval}")
+    ch = 3 if magic in (b"P3", b"P6") else 1
+    n = w * h * ch
+    if magic in (b"P5", b"P6"):
         pos += 1  # single whitespace byte after maxval
-        img = np.frombuffer(raw, dtype=np.uint8, count=w * h, offset=pos)
+        dt = np.dtype(">u2") if maxval > 255 else np.dtype(np.uint8)
+        if len(raw) - pos < n * dt.itemsize:
+            raise ValueError(f"{path}: expected {n} samples, file is too short")
+        img = np.frombuffer(raw, dtype=dt, count=n, offset=pos)
     else:
         body = re.sub(rb"#[^\n]*", b"", raw[pos:])
         img = np.array(body.split(), dtype=np.int64)
-        if img.size != w * h:
-            raise ValueError(f"{path}: expected {w*h} samples, found {img.size}")
-        img = img.astype(np.uint8)
-    return np.ascontiguousarray(img.reshape(h, w))
+        if img.size != n:
+            raise ValueError(f"{path}: expected {n} samples, found {img.size}")
+    img = _narrow(img, maxval)
+    return np.ascontiguousarray(img.reshape((h, w, 3) if ch == 3 else (h, w)))
+
+
+def read_pgm(path: str) -> np.ndarray:
+    """Grey PNM -> (H, W) uint8 (see :func:`read_pnm`)."""
+    img = read_pnm(path)
+    if img.ndim != 2:
+        raise ValueError(f"{path}: colour image where a grey one was expected")
+    return img
+
+
+def read_png(path: str):
+    """Minimal PNG reader (zlib is in the standard library; map_server loads PNGs through SDL_image):
+    non-interlaced, bit depth 8 or 16 (and 1/2/4 for grey / palette), colour types 0 grey, 2 RGB, 3 palette
+    (returned as palette INDICES, which is what map_server reads from SDL's 8-bit indexed surface),
+    4 grey+alpha, 6 RGBA.  Returns ((H, W) or (H, W, C) uint8, has_alpha)."""
+    import struct
+    import zlib
+    with open(path, "rb") as f:
+        raw = f.read()
+    if raw[:8] != b"\x89PNG\r\n\x1a\n":
+        raise ValueError(f"{path}: not a PNG")
+    pos, idat, hdr = 8, [], None
+    while pos + 8 <= len(raw):
+        length, kind = struct.unpack(">I4s", raw[pos:pos + 8])
+        body = raw[pos + 8:pos + 8 + length]
+        pos += 12 + length
+        if kind == b"IHDR":
+            hdr = struct.unpack(">IIBBBBB", body)
+        elif kind == b"IDAT":
+            idat.append(body)
+        elif kind == b"IEND":
+            break
+    if hdr is None:
+        raise ValueError(f"{path}: no IHDR")
+    w, h, depth, ctype, _, _, interlace = hdr
+    if interlace:
+        raise ValueError(f"{path}: interlaced PNG not supported")
+    ch = {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}.get(ctype)
+    if ch is None or depth not in (1, 2, 4, 8, 16) or (depth < 8 and ctype not in (0, 3)):
+        raise ValueError(f"{path}: unsupported PNG colour type {ctype} / depth {depth}")
+    data = zlib.decompress(b"".join(idat))
+    bpp = max(1, ch * depth // 8)                 # bytes per complete pixel, for the filters
+    stride = (w * ch * depth + 7) // 8
+    rows = np.zeros((h, stride), dtype=np.uint8)
+    prev = np.zeros(stride, dtype=np.int64)
+    for y in range(h):
+        ft = data[y * (stride + 1)]
+        line = np.frombuffer(data, dtype=np.uint8, count=stride, offset=y * (stride + 1) + 1).astype(np.int64)
+        if ft == 0:
+            cur = line
+        elif ft == 2:
+            cur = (line + prev) & 255
+        else:                                     # Sub / Average / Paeth depend on the pixel to the left
+            cur = np.zeros(stride, dtype=np.int64)
+            for x in range(stride):
+                a = cur[x - bpp] if x >= bpp else 0
+                b = prev[x]
+                if ft == 1:
+                    pred = a
+                elif ft == 3:
+                    pred = (a + b) >> 1
+                elif ft == 4:
+                    c = prev[x - bpp] if x >= bpp else 0
+                    pa, pb, pc = abs(b - c), abs(a - c), abs(a + b - 2 * c)
+                    pred = a if (pa <= pb and pa <= pc) else (b if pb <= pc else c)
+                else:
+                    raise ValueError(f"{path}: bad PNG filter {ft}")
+                cur[x] = (line[x] + pred) & 255
+        rows[y] = cur
+        prev = cur
+    if depth == 16:
+        img = _narrow(rows.reshape(h, w * ch, 2).astype(np.int64) @ np.array([256, 1]), 65535)
+    elif depth == 8:
+        img = rows
+    else:                                         # packed 1/2/4-bit samples, most significant first
+        bits = np.unpackbits(rows, axis=1)[:, :w * depth].reshape(h, w, depth)
+        vals = bits.astype(np.int64) @ (1 << np.arange(depth - 1, -1, -1))
+        img = vals.astype(np.uint8) if ctype == 3 else _narrow(vals, (1 << depth) - 1)
+    img = np.ascontiguousarray(img.reshape((h, w, ch) if ch > 1 else (h, w)).astype(np.uint8))
+    return img, ctype in (4, 6)
+
+
+def read_image(path: str):
+    """Any map image the loader understands -> ((H, W) or (H, W, C) uint8 rows top to bottom, has_alpha)."""
+    with open(path, "rb") as f:
+        magic = f.read(8)
+    if magic[:8] == b"\x89PNG\r\n\x1a\n":
+        return read_png(path)
+    if magic[:2] in (b"P2", b"P5", b"P3", b"P6"):
+        return read_pnm(path), False
+    raise ValueError(f"{path}: unsupported image format (PGM, PPM and PNG are read)")
 
 
 def write_pgm(path: str, img: np.ndarray) -> None:

@@ -21,7 +21,7 @@ import threading
 import numpy as np
 
 from . import _native
-from .maps import MapYaml, load_map_yaml, quaternion_to_yaw, read_pgm
+from .maps import MapYaml, load_map_yaml, quaternion_to_yaw, read_image
 
 
 MAP_MODES = {"trinary": 0, "scale": 1, "raw": 2}
@@ -182,12 +182,18 @@ class PyOMap:
         h = C.c_void_p()
         if isinstance(arg, (str, MapYaml)):
             y = load_map_yaml(arg) if isinstance(arg, str) else arg
-            img = read_pgm(y.image)
+            img, has_alpha = read_image(y.image)
             self._meta = (y.resolution, y.origin[0], y.origin[1], y.origin[2])
-            rc = L.rl_map_from_image(img.ctypes.data, img.shape[1], img.shape[0], y.negate,
-                                     y.occupied_thresh, y.free_thresh, MAP_MODES[y.mode], int(bool(binarise)),
-                                     y.resolution, y.origin[0], y.origin[1], y.origin[2],
-                                     self.device, C.byref(h))
+            if img.ndim == 2:
+                rc = L.rl_map_from_image(img.ctypes.data, img.shape[1], img.shape[0], y.negate,
+                                         y.occupied_thresh, y.free_thresh, MAP_MODES[y.mode], int(bool(binarise)),
+                                         y.resolution, y.origin[0], y.origin[1], y.origin[2],
+                                         self.device, C.byref(h))
+            else:   # colour / alpha: map_server averages the channels of every pixel first
+                rc = L.rl_map_from_image_channels(img.ctypes.data, img.shape[1], img.shape[0], img.shape[2],
+                                                  int(has_alpha), y.negate, y.occupied_thresh, y.free_thresh,
+                                                  MAP_MODES[y.mode], int(bool(binarise)), y.resolution,
+                                                  y.origin[0], y.origin[1], y.origin[2], self.device, C.byref(h))
         elif isinstance(arg, np.ndarray):
             if arg.ndim != 2:
                 raise ValueError("PyOMap: numpy occupancy grid must be 2-D")

@@ -56,8 +56,14 @@ class PeerGather:
     """
 
     def __init__(self, device_index: int, slot_rays: int, group: Optional[dist.ProcessGroup] = None,
-                 backend: str = "auto", multicast: bool = True, nbuf: int = 2):
+                 backend: str = "auto", multicast: Optional[bool] = None, nbuf: int = 2):
+        import os
         from . import _native
+        # RL_GATHER_MODE = mc (NVLS multicast, default) | mc_weak (multimem.st.weak) | uc (one store per peer)
+        gmode = os.environ.get("RL_GATHER_MODE", "mc")
+        if multicast is None:
+            multicast = gmode != "uc"
+        self._weak = gmode == "mc_weak"
         self._native = _native
         self.group = group
         self.world = dist.get_world_size(group)
@@ -103,7 +109,7 @@ class PeerGather:
         ok = torch.tensor([1 if mc else 0], dtype=torch.int32, device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
         if int(ok.item()) == 1:
-            self.flags = 1   # RL_GATHER_MULTICAST
+            self.flags = 3 if self._weak else 1   # RL_GATHER_MULTICAST (| RL_GATHER_WEAK)
             self._base_ptrs = [mc] + ptrs[1:]
         else:
             self._base_ptrs = ptrs

@@ -1,4 +1,5 @@
-"""Multi-GPU correctness check, run by hand on a box with >= 2 GPUs (not collected by pytest):
+"""Multi-GPU correctness check, spawned by tests/test_gpu_multi.py for world sizes 2 / 4 / 8 when the box has
+that many GPUs (or by hand):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \\
         --master-port 29555 tests/multigpu_check.py
@@ -17,8 +18,8 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pyracecarsimulator_b200 import maps, range_libc  # noqa: E402
 from pyracecarsimulator_b200.racecar import BatchedCar  # noqa: E402
-from pyracecarsimulator_b200.sharded import (ShardedRollout, ShardedScanner, gpu_march_fn, gpu_rollout_fn,  # noqa: E402
-                                             shard_bounds)
+from pyracecarsimulator_b200.sharded import (ShardedRollout, ShardedScanner, gpu_march_angles_fn, gpu_march_fn,  # noqa: E402
+                                             gpu_rollout_fn, shard_bounds)
 
 
 def main():
@@ -50,6 +51,63 @@ def main():
         ok = ok and all(checks)
         if rank == 0:
             print(f"n={n}: all={checks[0]} root={checks[1]} none={checks[2]} fused={checks[3]}")
+    # chunk-pipelined NCCL all-gather (piece k-1 travels while piece k is marched)
+    sc3 = ShardedScanner(gpu_march_fn(rm, fov, R), R, dev, chunks=3)
+    for n in (1001, 7):
+        poses = torch.from_numpy(maps.sample_free_poses(omap.dist(), n, 5 + n, y.resolution, y.origin))
+        want = torch.empty(n * R, dtype=torch.float32, device=dev)
+        rm.calc_range_fan(poses.to(dev), want, fov, R)
+        c = torch.equal(sc3.scan(poses, gather="all"), want)
+        ok = ok and c
+        if rank == 0:
+            print(f"n={n}: chunked all-gather={c}")
+    # the particle-filter shape (config 3): calc_range_repeat_angles sharded, NCCL and fused gathers
+    A = 60
+    angles = torch.from_numpy(np.linspace(-fov / 2, fov / 2, A, endpoint=False).astype(np.float32)).to(dev)
+    sca = ShardedScanner(gpu_march_angles_fn(rm, angles), A, dev)
+    for n in (4099, 64, 3):
+        poses = torch.from_numpy(maps.sample_free_poses(omap.dist(), n, 9 + n, y.resolution, y.origin))
+        want = torch.empty(n * A, dtype=torch.float32, device=dev)
+        rm.calc_range_repeat_angles(poses.to(dev), angles, want)
+        checks = [torch.equal(sca.scan(poses, gather="all"), want), torch.equal(sca.scan_fused(poses, rm, angles=angles), want)]
+        ok = ok and all(checks)
+        if rank == 0:
+            print(f"repeat_angles n={n}: nccl={checks[0]} fused={checks[1]}")
+    # back-to-back fused calls: the view of call i stays valid while call i+1 runs (two buffer sets)
+    pa = torch.from_numpy(maps.sample_free_poses(omap.dist(), 800, 1, y.resolution, y.origin))
+    pb = torch.from_numpy(maps.sample_free_poses(omap.dist(), 800, 2, y.resolution, y.origin))
+    wa = torch.empty(800 * R, dtype=torch.float32, device=dev)
+    wb = torch.empty(800 * R, dtype=torch.float32, device=dev)
+    rm.calc_range_fan(pa.to(dev), wa, fov, R)
+    rm.calc_range_fan(pb.to(dev), wb, fov, R)
+    scf = ShardedScanner(gpu_march_fn(rm, fov, R), R, dev)
+    c = True
+    for _ in range(4):
+        va = scf.scan_fused(pa, rm, fov)
+        vb = scf.scan_fused(pb, rm, fov)
+        c = c and torch.equal(va, wa) and torch.equal(vb, wb)
+    ok = ok and c
+    if rank == 0:
+        print(f"back-to-back fused views: {c}")
+    # a batch gathered in pieces through the alternating buffer sets (config 5's path)
+    n, piece = 1003, 100
+    poses = torch.from_numpy(maps.sample_free_poses(omap.dist(), n, 99, y.resolution, y.origin))
+    want = torch.empty(n * R, dtype=torch.float32, device=dev)
+    rm.calc_range_fan(poses.to(dev), want, fov, R)
+    per = -(-n // world)
+    got = torch.full((n * R,), -1.0, dtype=torch.float32, device=dev)
+    for first, counts, gathered in scf.scan_fused_chunks(poses, rm, fov, piece):
+        for r in range(world):
+            if counts[r] > 0:
+                a = (r * per + first) * R
+                got[a:a + counts[r] * R] = gathered[r, :counts[r] * R]
+    c = torch.equal(got, want)
+    ok = ok and c
+    if rank == 0:
+        print(f"gathered in pieces: {c}")
+    for s_ in (sca, scf):
+        if getattr(s_, "_peer", None) is not None:
+            s_._peer.close()
     # fused rollout, cars sharded (config 4 shape, reduced): 1001 / 5 / 1 cars x 30 steps x 270 beams
     car = BatchedCar(device=local)
     car.setCarEdgeDistances(R, -fov / 2.0, fov / R, 0.275)

@@ -285,3 +285,43 @@ def test_unknown_marcher_flag_is_rejected():
     range_libc.PyRayMarchingGPU(small, 300, flags=_native.RL_FLAG_NO_L2_WINDOW)
     with pytest.raises(ValueError):
         range_libc.PyRayMarchingGPU(small, 300, flags=0x80)
+
+
+# --------------------------------------------------------------------------- colour / alpha map images
+@pytest.mark.parametrize("fmt,ch,has_alpha", [("png", 3, False), ("png", 4, True), ("png", 2, True), ("ppm", 3, False)])
+@pytest.mark.parametrize("mode,negate", [("trinary", 0), ("scale", 0), ("scale", 1), ("raw", 1)])
+def test_colour_and_alpha_map_images(orc, tmp_path, fmt, ch, has_alpha, mode, negate):
+    """map_server averages the channels of a pixel before thresholding: the device LUT
+    over the channel sum against the oracle's per-pixel restatement, occupancy and d^2 bit-exact."""
+    from img_util import write_png
+    rng = np.random.default_rng(ch * 10 + negate)
+    img = rng.integers(0, 256, (70, 90, ch), dtype=np.uint8)
+    img[10:20, 30:70] = 2
+    img[rng.random((70, 90)) < 0.2, ch - 1] = 0
+    path = str(tmp_path / ("m." + fmt))
+    if fmt == "png":
+        write_png(path, img, {2: 4, 3: 2, 4: 6}[ch])
+    else:
+        with open(path, "wb") as f:
+            f.write(b"P6\n90 70\n255\n" + img.tobytes())
+    y = maps.MapYaml(path, 0.05, (0.0, 0.0, 0.0), negate, 0.65, 0.196, mode)
+    for binarise in (True, False):
+        omap = range_libc.PyOMap(y, binarise=binarise)
+        grid = orc.mapserver_occupancy_channels(img, has_alpha, negate, 0.65, 0.196, mode)
+        occ = orc.omap_from_grid(grid, binarise)
+        assert np.array_equal(omap.occupancy(), occ)
+        assert np.array_equal(omap.dist2(), orc.edt_exact(occ))
+
+
+def test_deep_pgm_and_raw_negate(orc, tmp_path):
+    rng = np.random.default_rng(8)
+    deep = rng.integers(0, 65536, (40, 50), dtype=np.uint16)
+    path = str(tmp_path / "deep.pgm")
+    with open(path, "wb") as f:
+        f.write(b"P5\n50 40\n65535\n" + deep.astype(">u2").tobytes())
+    img8 = ((deep.astype(np.int64) * 255 + 32767) // 65535).astype(np.uint8)
+    for mode, negate in (("trinary", 0), ("raw", 1), ("raw", 0)):
+        y = maps.MapYaml(path, 0.05, (0.0, 0.0, 0.0), negate, 0.65, 0.196, mode)
+        omap = range_libc.PyOMap(y, binarise=False)
+        occ = orc.omap_from_grid(orc.mapserver_occupancy(img8, negate, 0.65, 0.196, mode), False)
+        assert np.array_equal(omap.occupancy(), occ)

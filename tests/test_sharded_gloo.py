@@ -36,7 +36,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, n_poses, num_rays, gather, q):
+def _worker(rank, world, port, n_poses, num_rays, gather, q, chunks=1):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -55,7 +55,7 @@ def _worker(rank, world, port, n_poses, num_rays, gather, q):
             if p.shape[0]:
                 out.copy_(torch.from_numpy(m.calc_range_fan(p.numpy(), num_rays, 4.71)))
 
-        sc = ShardedScanner(march, num_rays, torch.device("cpu"))
+        sc = ShardedScanner(march, num_rays, torch.device("cpu"), chunks=chunks)
         got = sc.scan(torch.from_numpy(poses), gather=gather)
         want = m.calc_range_fan(poses, num_rays, 4.71) if n_poses else np.zeros(0, np.float32)
         if gather == "all":
@@ -70,13 +70,16 @@ def _worker(rank, world, port, n_poses, num_rays, gather, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n_poses,gather", [(2, 37, "all"), (2, 37, "root"), (2, 37, "none"),
-                                                  (3, 10, "all"), (2, 1, "all"), (2, 0, "all")])
-def test_sharded_scan_matches_single_process(world, n_poses, gather):
+@pytest.mark.parametrize("world,n_poses,gather,chunks", [(2, 37, "all", 1), (2, 37, "root", 1), (2, 37, "none", 1),
+                                                         (3, 10, "all", 1), (2, 1, "all", 1), (2, 0, "all", 1),
+                                                         # chunk-pipelined all-gather: piece k-1 travels while piece k is marched
+                                                         (2, 37, "all", 3), (3, 10, "all", 4), (2, 1, "all", 2), (2, 0, "all", 3),
+                                                         (2, 64, "all", 64)])
+def test_sharded_scan_matches_single_process(world, n_poses, gather, chunks):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n_poses, 60, gather, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_poses, 60, gather, q, chunks)) for r in range(world)]
     [p.start() for p in procs]
     [p.join(120) for p in procs]
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
