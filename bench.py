@@ -378,9 +378,28 @@ def run_native(args, rank, world, local_rank):
 
     # ---- N>1: the variants `value` does not time, same K steps each ----
     other_ms = {}
+    copy_ms = 0.0
     if dist_on:
         for how in ("none", "p2p", "allgather"):
             other_ms[how] = dev_ms if how == mode else timed(how)
+        # what the NVLink path alone takes for one step's bytes: the same stores without the march
+        rm.calc_range_fan(d_poses[0], d_out, FOV, B)
+        evs = events(torch, K)
+        for i in range(3):
+            peer.gather(d_out, stream_ptr)
+            peer.sync()
+        barrier()
+        for i in range(K):
+            cold_l2(i)
+            evs[i][0].record()
+            peer.gather(d_out, stream_ptr)
+            peer.sync()
+            evs[i][1].record()
+        barrier()
+        copy_ms = sum(a.elapsed_time(b) for a, b in evs)
+        ok = torch.equal(peer.tensor()[rank * n_rays:(rank + 1) * n_rays], d_out)
+        if reduce_sum([0.0 if ok else 1.0])[0]:
+            raise SystemExit("bench.py: rl_allgather_ranges left a wrong slot")
 
     # ---- steady state: K launches back to back under one event pair, no flush between them ----
     outs4 = [torch.empty(n_rays, dtype=torch.float32, device=dev) for _ in range(N_SETS)]
@@ -488,8 +507,8 @@ def run_native(args, rank, world, local_rank):
     d2h_min_alone = -reduce_max([-d2h_alone])[0]
     d2h_min_all = -reduce_max([-d2h_all])[0]
 
-    dev_ms, e2e_s, t_wall, ms_none, ms_p2p, ms_nccl = reduce_max(
-        [dev_ms, e2e_s, t_wall] + [other_ms.get(h, 0.0) for h in ("none", "p2p", "allgather")])
+    dev_ms, e2e_s, t_wall, ms_none, ms_p2p, ms_nccl, copy_ms = reduce_max(
+        [dev_ms, e2e_s, t_wall] + [other_ms.get(h, 0.0) for h in ("none", "p2p", "allgather")] + [copy_ms])
 
     # ---- roofline inputs (rank 0's launch): algorithmic bytes of ONE launch (4 B/step + 4 B/ray + 12 B/pose) ----
     roofline = None
@@ -563,6 +582,11 @@ def run_native(args, rank, world, local_rank):
                                   "achieved": recv / (ms_p2p / K * 1e-3) / 1e9, "peak": NVLINK_GBS, "unit": "GB/s",
                                   "frac": recv / (ms_p2p / K * 1e-3) / 1e9 / NVLINK_GBS,
                                   "floor_ms": recv / (NVLINK_GBS * 1e9) * 1e3,
+                                  "stores_only_ms": copy_ms / K,
+                                  "frac_of_stores_only": (copy_ms / K) / (ms_p2p / K) if ms_p2p else None,
+                                  "stores_only_note": "rl_allgather_ranges: the same NVLink stores of one step's ranges without "
+                                                      "the march (+ the same barrier), measured in this run: the practical floor "
+                                                      "of the gathered step on this box",
                                   "note": "fused gather step against NVLink ingress: every GPU must receive the other "
                                           f"{world - 1} shards; peak = nominal {NVLINK_GBS:.0f} GB/s per direction"}
 

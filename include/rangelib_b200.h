@@ -211,6 +211,11 @@ RL_API int32_t rl_calc_range_repeat_angles_allgather(rl_marcher *m, const float 
                                                      int64_t slot_rays, int64_t num_poses, int32_t num_angles,
                                                      uint32_t flags, void *stream);
 
+/* The all-gather alone, for ranges that already exist on this GPU: d_src[0..n) -> slot `rank` of every       */
+/* gathered buffer (same stores as the fused calls; d_src and rank*slot_rays 16-byte aligned).               */
+RL_API int32_t rl_allgather_ranges(int32_t device, const float *d_src, void *const *peer_bufs, int32_t world,
+                                   int32_t rank, int64_t slot_rays, int64_t n, uint32_t flags, void *stream);
+
 /* Number of distance-field loads ("march steps") the last *_host call performed, when the */
 /* marcher was asked to count them (rl_marcher_count_steps(m, 1)); used by the roofline.    */
 RL_API int32_t rl_marcher_count_steps(rl_marcher *m, int32_t enable);

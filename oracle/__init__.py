@@ -246,6 +246,19 @@ def car_step(params, state, speed, steer, dt=0.01):
     return state
 
 
+def car_rollout_poses(params, states, actions, steps, every=10, dt=0.01):
+    """Vehicle half of MCTS.rollout for many cars on the CPU: returns the (steps, n, 3) float32 base-link poses
+    (step-major, like the device rollout); ``states`` (n, 11) float64 is updated in place."""
+    states = np.ascontiguousarray(states, dtype=np.float64)
+    actions = np.ascontiguousarray(actions, dtype=np.float64)
+    n = states.shape[0]
+    poses = np.empty((steps, n, 3), dtype=np.float32)
+    f = lib().orc_car_rollout_poses
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_void_p]
+    f(C.byref(params), states.ctypes.data, actions.ctypes.data, n, int(steps), int(every), float(dt), poses.ctypes.data)
+    return poses, states
+
+
 def car_scan_pose(state, scan_dist_to_base):
     pose = np.empty(3, dtype=np.float64)
     lib().orc_car_scan_pose(state, scan_dist_to_base, pose)

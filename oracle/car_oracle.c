@@ -95,6 +95,27 @@ ORC_EXPORT void orc_car_step(const orc_car_params *p, double *st, double in_spee
     st[5] = w; st[6] = beta; st[7] = dyn ? 1.0 : 0.0;
 }
 
+/* MCTS.rollout's vehicle half for many cars (scripts/mcts.py:202-235): `steps` updatePosition(dt) per car with a
+ * new (speed, steer) from actions[(c, i / every)] every `every`-th step; records the base-link pose after each
+ * step narrowed to fp32 where the reference narrows it (the f32 pose buffer, mcts.py:211, :229-231), step-major
+ * (steps, n, 3) like the device rollout.  states (n, 11) is updated in place. */
+ORC_EXPORT void orc_car_rollout_poses(const orc_car_params *p, double *states, const double *actions, int64_t n,
+                                      int steps, int every, double dt, float *poses)
+{
+    const int n_act = (steps + every - 1) / every;
+    for (int64_t c = 0; c < n; ++c) {
+        double *st = states + 11 * c;
+        for (int i = 0; i < steps; ++i) {
+            const double *a = actions + 2 * ((int64_t)n_act * c + i / every);
+            orc_car_step(p, st, a[0], a[1], dt);
+            float *o = poses + 3 * ((int64_t)i * n + c);
+            o[0] = (float)st[0];
+            o[1] = (float)st[1];
+            o[2] = (float)st[2];
+        }
+    }
+}
+
 ORC_EXPORT void orc_car_scan_pose(const double *st, double scan_dist_to_base, double *pose)
 {
     pose[0] = st[0] + scan_dist_to_base * cos(st[2]);

@@ -66,6 +66,7 @@ SIGNATURES = {
     "rl_peer_free": (_i32, [_i32, _vp]),
     "rl_calc_range_fan_allgather": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _i64, _i64, _i32, _f, C.c_uint32, _vp]),
     "rl_calc_range_repeat_angles_allgather": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _i64, _i32, C.c_uint32, _vp]),
+    "rl_allgather_ranges": (_i32, [_i32, _vp, _vp, _i32, _i32, _i64, _i64, C.c_uint32, _vp]),
     "rl_marcher_set_pipelined": (_i32, [_vp, _i32]),
     "rl_marcher_join": (_i32, [_vp, _vp]),
     "rl_marcher_count_steps": (_i32, [_vp, _i32]),

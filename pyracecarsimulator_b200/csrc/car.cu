@@ -245,6 +245,7 @@ march_crash_kernel(rl::MarchParams P, const float *__restrict__ poses, const dou
                    float fov, float inc, double thresh, uint32_t *first, float *__restrict__ outs)
 {
     asm volatile("griddepcontrol.launch_dependents;");
+    if (blockIdx.y == 0 && blockIdx.z == 0) rl::prefetch_field(P, blockIdx.x, threadIdx.x);
     const uint32_t idx = blockIdx.x * rl::MARCH_CTA_THREADS + threadIdx.x;
     const int64_t outer = (int64_t)blockIdx.z * gridDim.y + blockIdx.y;
     if (idx >= inner_rays || outer >= outer_count) return;

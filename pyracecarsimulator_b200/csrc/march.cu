@@ -39,6 +39,7 @@ march_many_kernel(MarchParams P, const float *__restrict__ ins, float *__restric
                   int64_t n, unsigned long long *counter)
 {
     release_dependents();
+    rl::prefetch_field(P, blockIdx.x, threadIdx.x);
     const int64_t i = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
     uint32_t steps = 0;
     if (i < n) {
@@ -111,6 +112,7 @@ march_pose_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_s
                   PeerOut peers = PeerOut{})
 {
     release_dependents();
+    rl::prefetch_field(P, blockIdx.x, threadIdx.x);
     __shared__ float stage[OUT == OUT_PEERS4 ? CTA_THREADS : 1];
     const int64_t i = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
     uint32_t steps = 0;
@@ -152,6 +154,20 @@ march_pose_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_s
         }
     }
     flush_steps<COUNT>(steps, counter);
+}
+
+// Ranges that already exist on this GPU -> slot `rank` of every GPU's gathered buffer (16-byte stores).  The
+// same stores as the fused march without the march: what the NVLink / NVSwitch path alone takes for these
+// bytes (bench.py reports the fused step against it), and the gather for ranges produced by other means.
+__global__ void __launch_bounds__(256)
+gather_copy_kernel(const float *__restrict__ src, int64_t n, PeerOut peers)
+{
+    const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 + 3 < n) {
+        peer_store4(peers, i4, *reinterpret_cast<const float4 *>(src + i4));
+    } else {
+        for (int64_t i = i4; i < n; ++i) peer_store(peers, i, src[i]);
+    }
 }
 
 __global__ void trig_probe_kernel(const float *__restrict__ in, float *__restrict__ s,
@@ -421,6 +437,9 @@ int32_t rl_marcher_create(const rl_map *map, float max_range_px, uint32_t flags,
             if (cur >= field || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, field) == cudaSuccess) {
                 m->l2_window_bytes = field;
                 m->l2_hit_ratio = 1.0f;
+                // RL_FIELD_PREFETCH=0 turns the launch-time L2 prefetch of the field off (measurements)
+                const char *pe = std::getenv("RL_FIELD_PREFETCH");
+                m->P.prefetch_bytes = (pe && pe[0] == '0') ? 0u : (uint32_t)field;
                 m->l2_limit_raised = true;
                 ++cv.users;
             }
@@ -635,6 +654,28 @@ int32_t rl_calc_range_repeat_angles_allgather(rl_marcher *m, const float *d_pose
     if (rc != RL_OK) return rc;
     return launch_pose<false>(m, d_poses, 1, d_angles, nullptr, num_poses, num_angles, 0.0f, (cudaStream_t)stream,
                               false, &po);
+}
+
+// All-gather of ranges that already exist: d_src[0..n) -> slot `rank` of every gathered buffer.
+int32_t rl_allgather_ranges(int32_t device, const float *d_src, void *const *peer_bufs, int32_t world, int32_t rank,
+                            int64_t slot_rays, int64_t n, uint32_t flags, void *stream)
+{
+    if (!peer_bufs || world < 1 || world > MAX_PEERS || rank < 0 || rank >= world || n < 0 || n > slot_rays ||
+        (n > 0 && !d_src))
+        return rl::fail(RL_ERR_BAD_ARG, "rl_allgather_ranges: bad argument");
+    if (n == 0) return RL_OK;
+    if ((reinterpret_cast<uintptr_t>(d_src) & 15) || ((int64_t)rank * slot_rays) % 4)
+        return rl::fail(RL_ERR_BAD_ARG, "rl_allgather_ranges: source and slot must be 16-byte aligned");
+    rl::DeviceGuard guard(device);
+    if (!guard.ok) return rl::fail(RL_ERR_NO_DEVICE, "rl_allgather_ranges: bad device");
+    PeerOut po{};
+    const int32_t rc = fill_peers(po, peer_bufs, world, rank, slot_rays, flags, "rl_allgather_ranges");
+    if (rc != RL_OK) return rc;
+    const int64_t blocks = ((n + 3) / 4 + 255) / 256;
+    if (blocks > 0x7fffffffLL) return rl::fail(RL_ERR_BAD_ARG, "rl_allgather_ranges: too many ranges for one call");
+    gather_copy_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_src, n, po);
+    RL_CUDA(cudaGetLastError());
+    return RL_OK;
 }
 
 int32_t rl_calc_range_many_host(rl_marcher *m, const float *ins, float *outs, int64_t n)

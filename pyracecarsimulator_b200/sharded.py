@@ -171,6 +171,13 @@ class PeerGather:
             marcher._h, poses.data_ptr(), angles.data_ptr(), self._take(buf), self.world, self.rank, self.slot_rays,
             n, int(na), self.flags, stream_ptr), "rl_calc_range_repeat_angles_allgather")
 
+    def gather(self, ranges: torch.Tensor, stream_ptr: int, buf: Optional[int] = None):
+        """The all-gather alone: ranges that already exist on this GPU go to slot ``rank`` of every GPU's next
+        buffer set through the same NVLink stores (``rl_allgather_ranges``)."""
+        self._native.check(self._native.lib().rl_allgather_ranges(
+            self.device_index, ranges.data_ptr(), self._take(buf), self.world, self.rank, self.slot_rays,
+            ranges.numel(), self.flags, stream_ptr), "rl_allgather_ranges")
+
     def sync(self):
         """Stream-ordered barrier: returns (on the stream) once every rank's march has completed."""
         if self._hdl is not None:

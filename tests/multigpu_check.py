@@ -89,6 +89,19 @@ def main():
     ok = ok and c
     if rank == 0:
         print(f"back-to-back fused views: {c}")
+    # the all-gather alone (ranges that already exist): slot r of every GPU == rank r's shard
+    lo, hi = shard_bounds(800, world, rank)
+    per = -(-800 // world)
+    peer = scf._peer
+    mine = wa[lo * R:hi * R].contiguous()
+    peer.gather(mine, int(torch.cuda.current_stream(local).cuda_stream))
+    peer.sync()
+    g = peer.tensor()
+    c = all(torch.equal(g[r * peer.slot_rays: r * peer.slot_rays + (min(800, (r + 1) * per) - r * per) * R],
+                        wa[r * per * R: min(800, (r + 1) * per) * R]) for r in range(world))
+    ok = ok and c
+    if rank == 0:
+        print(f"all-gather of existing ranges: {c}")
     # a batch gathered in pieces through the alternating buffer sets (config 5's path)
     n, piece = 1003, 100
     poses = torch.from_numpy(maps.sample_free_poses(omap.dist(), n, 99, y.resolution, y.origin))

@@ -214,6 +214,32 @@ def test_fused_allgather_repeat_angles_two_virtual_ranks(big, B, R):
             L.rl_peer_free(0, p)
 
 
+def test_allgather_of_existing_ranges_two_virtual_ranks():
+    import torch
+    from pyracecarsimulator_b200.sharded import _DevicePtr
+    L = _native.lib()
+    n, slot = 1001, 1004
+    bufs = []
+    try:
+        for _ in range(2):
+            p, h = C.c_void_p(), (C.c_uint8 * 64)()
+            _native.check(L.rl_peer_alloc(0, 2 * slot * 4, C.byref(p), h))
+            bufs.append(p)
+        ptrs = (C.c_void_p * 2)(bufs[0].value, bufs[1].value)
+        src = [torch.rand(n, device="cuda"), torch.rand(n, device="cuda")]
+        for r in range(2):
+            _native.check(L.rl_allgather_ranges(0, src[r].data_ptr(), ptrs, 2, r, slot, n, 0, None))
+        torch.cuda.synchronize()
+        for r in range(2):
+            got = torch.as_tensor(_DevicePtr(bufs[r].value, 2 * slot), device="cuda")
+            assert torch.equal(got[:n], src[0]) and torch.equal(got[slot:slot + n], src[1])
+        assert L.rl_allgather_ranges(0, src[0].data_ptr(), ptrs, 2, 1, 1001, n, 0, None) == _native.RL_ERR_BAD_ARG   # misaligned slot
+        assert L.rl_allgather_ranges(0, src[0].data_ptr(), ptrs, 2, 0, 100, n, 0, None) == _native.RL_ERR_BAD_ARG    # slot too small
+    finally:
+        for p in bufs:
+            L.rl_peer_free(0, p)
+
+
 # --------------------------------------------------------------------------- host buffers
 def test_growing_view_over_a_registered_buffer_takes_the_staged_path(big):
     """`big[:n1]` gets page-locked on its second sighting; a later, longer `big[:n2]` starts in
