@@ -75,6 +75,10 @@ typedef enum rl_status {
 /* device un-pins the lines and restores the previous limit.  An embedding application that manages  */
 /* the carve-out itself passes this flag.                                                            */
 #define RL_FLAG_NO_L2_WINDOW 1u
+/* Do not build the marcher's NaN-padded copy of the march field (it costs (rows + 2p)(cols + 2p) floats with  */
+/* p = ceil(max_range_px) + 16 and removes the per-step bounds test); the bounds-tested kernels are used,      */
+/* as they are automatically for max_range_px > 2048.  Results are identical either way.                     */
+#define RL_FLAG_NO_PADDED_FIELD 2u
 
 /* dist2 value of a cell from which no occupied cell is reachable (empty map) */
 #define RL_DIST2_INF 0x3fffffff

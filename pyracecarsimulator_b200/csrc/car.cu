@@ -238,14 +238,13 @@ crash_from_rays_kernel(const float *__restrict__ rays, const double *__restrict_
 // march_pose_kernel (profiles/r01_tuning.md sections 2 and 4).  The ray index is split so that it never
 // needs a 64-bit divide: blockIdx.y/z select the OUTER unit (the step when step-major, the group when
 // group-major), blockIdx.x * 128 + thread runs over the inner_poses * num_rays rays of that unit.
-template <bool WRITE, bool STEP_MAJOR>
+template <bool WRITE, bool STEP_MAJOR, bool PADDED>
 __global__ void __launch_bounds__(rl::MARCH_CTA_THREADS)
 march_crash_kernel(rl::MarchParams P, const float *__restrict__ poses, const double *__restrict__ edge,
                    uint32_t inner_rays, int num_rays, rl::FastDiv div, int64_t inner_poses, int64_t outer_count,
                    float fov, float inc, double thresh, uint32_t *first, float *__restrict__ outs)
 {
     asm volatile("griddepcontrol.launch_dependents;");
-    if (blockIdx.y == 0 && blockIdx.z == 0) rl::prefetch_field(P, blockIdx.x, threadIdx.x);
     const uint32_t idx = blockIdx.x * rl::MARCH_CTA_THREADS + threadIdx.x;
     const int64_t outer = (int64_t)blockIdx.z * gridDim.y + blockIdx.y;
     if (idx >= inner_rays || outer >= outer_count) return;
@@ -263,7 +262,7 @@ march_crash_kernel(rl::MarchParams P, const float *__restrict__ poses, const dou
     float s, c;
     rl::glibc_sincosf(thg, &s, &c);
     uint32_t steps = 0;
-    const float r = __fmul_rn(rl::march_ray<false>(P, gp.y, gp.x, c, s, steps, f0), P.w.scale);
+    const float r = __fmul_rn(rl::march_ray<false, PADDED>(P, gp.y, gp.x, c, s, steps, f0), P.w.scale);
     if (WRITE) outs[k * num_rays + j] = r;
     if (((double)r - __ldg(edge + j)) < thresh) atomicMin(first + g, pose_in_group);
 }
@@ -322,7 +321,7 @@ int32_t launch_march_crash(rl_marcher *m, const rl_car *car, const float *d_pose
     cudaLaunchAttribute attr[1];
     if (m->l2_window_bytes) {   // keep the distance field pinned in L2, as every march launch does
         attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-        attr[0].val.accessPolicyWindow.base_ptr = const_cast<float *>(m->P.dist);
+        attr[0].val.accessPolicyWindow.base_ptr = const_cast<float *>(m->d_field ? m->d_field : m->P.dist);
         attr[0].val.accessPolicyWindow.num_bytes = m->l2_window_bytes;
         attr[0].val.accessPolicyWindow.hitRatio = m->l2_hit_ratio;
         attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
@@ -330,9 +329,14 @@ int32_t launch_march_crash(rl_marcher *m, const rl_car *car, const float *d_pose
         cfg.attrs = attr;
         cfg.numAttrs = 1;
     }
-    RL_CUDA(cudaLaunchKernelEx(&cfg, march_crash_kernel<WRITE, STEP_MAJOR>, m->P, d_poses, (const double *)car->d_edge,
-                               (uint32_t)inner_rays, car->num_rays, fast_div_for(car->num_rays), inner_poses, outer_count,
-                               fov, fov / (float)car->num_rays, car->p.crash_thresh, d_first, d_ranges));
+    if (m->P.pad > 0)
+        RL_CUDA(cudaLaunchKernelEx(&cfg, march_crash_kernel<WRITE, STEP_MAJOR, true>, m->P, d_poses, (const double *)car->d_edge,
+                                   (uint32_t)inner_rays, car->num_rays, fast_div_for(car->num_rays), inner_poses, outer_count,
+                                   fov, fov / (float)car->num_rays, car->p.crash_thresh, d_first, d_ranges));
+    else
+        RL_CUDA(cudaLaunchKernelEx(&cfg, march_crash_kernel<WRITE, STEP_MAJOR, false>, m->P, d_poses, (const double *)car->d_edge,
+                                   (uint32_t)inner_rays, car->num_rays, fast_div_for(car->num_rays), inner_poses, outer_count,
+                                   fov, fov / (float)car->num_rays, car->p.crash_thresh, d_first, d_ranges));
     return RL_OK;
 }
 

@@ -60,32 +60,17 @@ __device__ __forceinline__ float march_step_of(float d)
 
 // Passed by value to every march kernel.
 struct MarchParams {
-    const float *dist;  // the march field step[row * cols + col] (see march_step_of), fp32 pixels
+    const float *dist;  // the march field (see march_step_of): cell (row, col) is dist[row * stride + col]
     int rows, cols;     // rows = OMap.width (msg.info.height), cols = OMap.height (msg.info.width)
+    int stride;         // floats between rows: cols, or cols + 2*pad for the marcher's padded copy
+    int pad;            // > 0: `pad` cells of NaN surround the map on every side (rows -pad .. rows+pad-1 and
+                        // columns -pad .. cols+pad-1 are addressable), and pad exceeds max_range + the tail
+                        // look-ahead, so no sample of a ray that starts inside the map needs a bounds test
     float frows, fcols;
     float max_range;    // pixels
     WorldFrame w;
-    // bytes of the field the first CTAs of a launch ask L2 to fetch (0 = none): an L2-sized field that is not
-    // resident (first use, or evicted by other work between scans) then streams in from HBM at copy speed
-    // instead of one demand miss at a time
-    uint32_t prefetch_bytes;
 };
 
-#ifdef __CUDACC__
-constexpr uint32_t PREFETCH_CHUNK = 16384;
-// CTA b asks for chunk b of the field (one bulk L2 prefetch by one thread); no-op beyond the field.
-__device__ __forceinline__ void prefetch_field(const MarchParams &P, uint32_t cta, uint32_t thread)
-{
-    if (thread != 0 || P.prefetch_bytes == 0) return;
-    const uint64_t off = (uint64_t)cta * PREFETCH_CHUNK;
-    if (off >= P.prefetch_bytes) return;
-    const uint32_t left = P.prefetch_bytes - (uint32_t)off;
-    const uint32_t bytes = (left < PREFETCH_CHUNK ? left : PREFETCH_CHUNK) & ~15u;
-    if (bytes)
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char *>(P.dist) + off), "r"(bytes)
-                     : "memory");
-}
-#endif
 
 }  // namespace rl
 

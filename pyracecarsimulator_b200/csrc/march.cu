@@ -2,6 +2,7 @@
 // Replaces range_libc's RayMarching / RayMarchingGPU calc_range_many (2-arg and the fork's
 // 4-arg fan) and calc_range_repeat_angles; reference call sites scripts/scan_simulator.py:103-106,
 // :130-133 and scripts/two_player/scan.py:69-70.
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -33,13 +34,12 @@ __device__ __forceinline__ void flush_steps(uint32_t steps, unsigned long long *
 }
 
 // ---- one (x, y, theta) row per ray (upstream 2-arg calc_range_many) ----
-template <bool COUNT>
+template <bool COUNT, bool PADDED>
 __global__ void __launch_bounds__(CTA_THREADS)
 march_many_kernel(MarchParams P, const float *__restrict__ ins, float *__restrict__ outs,
                   int64_t n, unsigned long long *counter)
 {
     release_dependents();
-    rl::prefetch_field(P, blockIdx.x, threadIdx.x);
     const int64_t i = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
     uint32_t steps = 0;
     if (i < n) {
@@ -47,7 +47,7 @@ march_many_kernel(MarchParams P, const float *__restrict__ ins, float *__restric
         const rl::FirstSample f0 = rl::first_sample(P, g.y, g.x);
         float s, c;
         rl::glibc_sincosf(g.theta, &s, &c);
-        outs[i] = __fmul_rn(rl::march_ray<COUNT>(P, g.y, g.x, c, s, steps, f0), P.w.scale);
+        outs[i] = __fmul_rn(rl::march_ray<COUNT, PADDED>(P, g.y, g.x, c, s, steps, f0), P.w.scale);
     }
     flush_steps<COUNT>(steps, counter);
 }
@@ -104,15 +104,14 @@ __device__ __forceinline__ void peer_store4(const PeerOut &peers, int64_t i, flo
     }
 }
 
-template <bool FAN, bool COUNT, bool SMALL, int OUT = OUT_LOCAL>
+template <bool FAN, bool COUNT, bool SMALL, int OUT, bool PADDED>
 __global__ void __launch_bounds__(CTA_THREADS)
 march_pose_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_stride_floats,
                   const float *__restrict__ angles, float *__restrict__ outs, int64_t num_rays_total,
                   int num_beams, rl::FastDiv div, float fov, float inc, unsigned long long *counter,
-                  PeerOut peers = PeerOut{})
+                  PeerOut peers)
 {
     release_dependents();
-    rl::prefetch_field(P, blockIdx.x, threadIdx.x);
     __shared__ float stage[OUT == OUT_PEERS4 ? CTA_THREADS : 1];
     const int64_t i = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
     uint32_t steps = 0;
@@ -136,7 +135,7 @@ march_pose_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_s
         const rl::FirstSample f0 = rl::first_sample(P, g.y, g.x);
         float s, c;
         rl::glibc_sincosf(thg, &s, &c);
-        const float r = __fmul_rn(rl::march_ray<COUNT>(P, g.y, g.x, c, s, steps, f0), P.w.scale);
+        const float r = __fmul_rn(rl::march_ray<COUNT, PADDED>(P, g.y, g.x, c, s, steps, f0), P.w.scale);
         if (OUT == OUT_PEERS) peer_store(peers, i, r);
         else if (OUT == OUT_PEERS4) stage[threadIdx.x] = r;
         else outs[i] = r;
@@ -154,6 +153,19 @@ march_pose_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_s
         }
     }
     flush_steps<COUNT>(steps, counter);
+}
+
+// Surround the map's march field with `pad` cells of NaN (see march_ray<.., PADDED>).
+__global__ void __launch_bounds__(256)
+pad_field_kernel(const float *__restrict__ src, int rows, int cols, int pad, float *__restrict__ dst)
+{
+    const int stride = cols + 2 * pad;
+    const int64_t total = (int64_t)(rows + 2 * pad) * stride;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int r = (int)(i / stride) - pad, c = (int)(i % stride) - pad;
+    dst[i] = ((unsigned)r < (unsigned)rows && (unsigned)c < (unsigned)cols) ? src[(size_t)r * cols + c]
+                                                                            : __int_as_float(0x7fc00000);
 }
 
 // Ranges that already exist on this GPU -> slot `rank` of every GPU's gathered buffer (16-byte stores).  The
@@ -222,8 +234,14 @@ int32_t launch_many(rl_marcher *m, const float *d_ins, float *d_outs, int64_t n,
     const int64_t blocks = (n + CTA_THREADS - 1) / CTA_THREADS;
     if (blocks > 0x7fffffffLL) return rl::fail(RL_ERR_BAD_ARG, "calc_range_many: too many rays for one call");
     unsigned long long *ctr = m->count ? m->d_steps : nullptr;
-    if (m->count) RL_CUDA(launch_windowed(m, march_many_kernel<true>, (unsigned)blocks, s, pdl, m->P, d_ins, d_outs, n, ctr));
-    else RL_CUDA(launch_windowed(m, march_many_kernel<false>, (unsigned)blocks, s, pdl, m->P, d_ins, d_outs, n, ctr));
+    const bool padded = m->P.pad > 0;
+    if (m->count) {
+        if (padded) RL_CUDA(launch_windowed(m, march_many_kernel<true, true>, (unsigned)blocks, s, pdl, m->P, d_ins, d_outs, n, ctr));
+        else RL_CUDA(launch_windowed(m, march_many_kernel<true, false>, (unsigned)blocks, s, pdl, m->P, d_ins, d_outs, n, ctr));
+    } else {
+        if (padded) RL_CUDA(launch_windowed(m, march_many_kernel<false, true>, (unsigned)blocks, s, pdl, m->P, d_ins, d_outs, n, ctr));
+        else RL_CUDA(launch_windowed(m, march_many_kernel<false, false>, (unsigned)blocks, s, pdl, m->P, d_ins, d_outs, n, ctr));
+    }
     RL_CUDA(cudaGetLastError());
     return RL_OK;
 }
@@ -256,9 +274,11 @@ int32_t launch_pose(rl_marcher *m, const float *d_poses, int64_t stride_rows, co
     unsigned long long *ctr = m->count ? m->d_steps : nullptr;
     const int64_t stride_floats = stride_rows * 3;
     const PeerOut po = peers ? *peers : PeerOut{};
-#define RL_LAUNCH(COUNT, SMALL, OUT)                                                               \
-    RL_CUDA(launch_windowed(m, march_pose_kernel<FAN, COUNT, SMALL, OUT>, (unsigned)blocks, s, pdl, m->P, d_poses, \
+#define RL_LAUNCH2(COUNT, SMALL, OUT, PADDED)                                                      \
+    RL_CUDA(launch_windowed(m, march_pose_kernel<FAN, COUNT, SMALL, OUT, PADDED>, (unsigned)blocks, s, pdl, m->P, d_poses, \
                             stride_floats, d_angles, d_outs, total, num_beams, div, fov, inc, ctr, po))
+#define RL_LAUNCH(COUNT, SMALL, OUT)                                                               \
+    do { if (m->P.pad > 0) RL_LAUNCH2(COUNT, SMALL, OUT, true); else RL_LAUNCH2(COUNT, SMALL, OUT, false); } while (0)
     if (peers) {
         // 16-byte stores need this rank's slot to start on a 16-byte boundary; RL_GATHER_VEC=0 forces 4-byte stores
         static const bool vec_ok = [] { const char *e = std::getenv("RL_GATHER_VEC"); return !(e && e[0] == '0'); }();
@@ -270,6 +290,7 @@ int32_t launch_pose(rl_marcher *m, const float *d_poses, int64_t stride_rows, co
     } else {
         if (small) RL_LAUNCH(false, true, OUT_LOCAL); else RL_LAUNCH(false, false, OUT_LOCAL);
     }
+#undef RL_LAUNCH2
 #undef RL_LAUNCH
     RL_CUDA(cudaGetLastError());
     return RL_OK;
@@ -404,7 +425,7 @@ int32_t rl_marcher_create(const rl_map *map, float max_range_px, uint32_t flags,
 {
     if (!map || !out) return rl::fail(RL_ERR_BAD_ARG, "rl_marcher_create: null pointer");
     if (!(max_range_px > 0.0f)) return rl::fail(RL_ERR_BAD_ARG, "rl_marcher_create: max_range_px must be > 0");
-    if (flags & ~(uint32_t)RL_FLAG_NO_L2_WINDOW) return rl::fail(RL_ERR_BAD_ARG, "rl_marcher_create: unknown flag");
+    if (flags & ~(uint32_t)(RL_FLAG_NO_L2_WINDOW | RL_FLAG_NO_PADDED_FIELD)) return rl::fail(RL_ERR_BAD_ARG, "rl_marcher_create: unknown flag");
     rl::DeviceGuard guard(map->device);
     if (!guard.ok) return rl::fail(RL_ERR_CUDA, "rl_marcher_create: cudaSetDevice failed");
     rl_marcher *m = new (std::nothrow) rl_marcher();
@@ -415,10 +436,33 @@ int32_t rl_marcher_create(const rl_map *map, float max_range_px, uint32_t flags,
     m->P.dist = map->d_step;
     m->P.rows = map->rows;
     m->P.cols = map->cols;
+    m->P.stride = map->cols;
+    m->P.pad = 0;
     m->P.frows = (float)map->rows;
     m->P.fcols = (float)map->cols;
     m->P.max_range = max_range_px;
     m->P.w = map->world;
+    // The marcher's own copy of the march field, surrounded by NaN far enough that no sample of a ray can fall
+    // outside it (march_ray<.., PADDED>): every sample lies within max_range (+1 for the truncation) of a pose
+    // inside the map, the tail look-ahead TAIL_AHEAD further.  Very long ranges keep the bounds-tested kernels.
+    if (!(flags & RL_FLAG_NO_PADDED_FIELD) && max_range_px <= 2048.0f) {
+        const int pad = (int)std::ceil(max_range_px) + rl::TAIL_AHEAD + 4;
+        const int64_t stride = (int64_t)map->cols + 2 * pad, prow = (int64_t)map->rows + 2 * pad;
+        if (prow * stride < ((int64_t)1 << 31) && cudaMalloc(&m->d_field, (size_t)(prow * stride) * sizeof(float)) == cudaSuccess) {
+            const int64_t total = prow * stride;
+            pad_field_kernel<<<(unsigned)((total + 255) / 256), 256>>>(map->d_step, map->rows, map->cols, pad, m->d_field);
+            if (cudaDeviceSynchronize() == cudaSuccess) {
+                m->P.dist = m->d_field + (int64_t)pad * stride + pad;   // cell (0, 0)
+                m->P.stride = (int)stride;
+                m->P.pad = pad;
+                m->field_bytes = (size_t)total * sizeof(float);
+            } else {
+                cudaFree(m->d_field);
+                m->d_field = nullptr;
+            }
+        }
+        cudaGetLastError();
+    }
     cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, map->device);
     if (!(flags & RL_FLAG_NO_L2_WINDOW) && map->device < 64) {
         // persisting-L2 carve-out large enough for the distance field: a device-wide limit, raised here and put
@@ -426,7 +470,7 @@ int32_t rl_marcher_create(const rl_map *map, float max_range_px, uint32_t flags,
         int max_persist = 0, max_window = 0;
         cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, map->device);
         cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, map->device);
-        const size_t field = (size_t)map->rows * map->cols * sizeof(float);
+        const size_t field = m->field_bytes ? m->field_bytes : (size_t)map->rows * map->cols * sizeof(float);
         std::lock_guard<std::mutex> lock(g_l2_mu);
         L2Carve &cv = g_l2[map->device];
         size_t cur = 0;
@@ -437,9 +481,6 @@ int32_t rl_marcher_create(const rl_map *map, float max_range_px, uint32_t flags,
             if (cur >= field || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, field) == cudaSuccess) {
                 m->l2_window_bytes = field;
                 m->l2_hit_ratio = 1.0f;
-                // RL_FIELD_PREFETCH=0 turns the launch-time L2 prefetch of the field off (measurements)
-                const char *pe = std::getenv("RL_FIELD_PREFETCH");
-                m->P.prefetch_bytes = (pe && pe[0] == '0') ? 0u : (uint32_t)field;
                 m->l2_limit_raised = true;
                 ++cv.users;
             }
@@ -471,7 +512,7 @@ int32_t rl_marcher_destroy(rl_marcher *m)
             if (m->done_ev[i]) cudaEventDestroy(m->done_ev[i]);
         }
         cudaFreeHost(m->h_in); cudaFreeHost(m->h_out);
-        cudaFree(m->d_in); cudaFree(m->d_out); cudaFree(m->d_angles); cudaFree(m->d_steps);
+        cudaFree(m->d_in); cudaFree(m->d_out); cudaFree(m->d_angles); cudaFree(m->d_steps); cudaFree(m->d_field);
         if (m->l2_limit_raised) {
             std::lock_guard<std::mutex> lock(g_l2_mu);
             L2Carve &cv = g_l2[m->map->device];

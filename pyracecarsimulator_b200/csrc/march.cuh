@@ -53,7 +53,7 @@ __device__ __forceinline__ FirstSample first_sample(const MarchParams &P, float 
     f.px = __float2int_rz(x0);   // fmaf(dx, 0, x0) == x0 for every finite dx
     f.py = __float2int_rz(y0);
     f.inside = (x0 == x0) && (y0 == y0) && (unsigned)f.px < (unsigned)P.rows && (unsigned)f.py < (unsigned)P.cols;
-    f.s = f.inside ? __ldg(P.dist + (f.px * P.cols + f.py)) : 0.0f;
+    f.s = f.inside ? __ldg(P.dist + (f.px * P.stride + f.py)) : 0.0f;
     return f;
 }
 
@@ -61,7 +61,13 @@ __device__ __forceinline__ FirstSample first_sample(const MarchParams &P, float 
 // elsewhere -- exactly the value the reference's loop adds to t after sampling the cell, computed once
 // per cell by the ingest with the same two fp32 operations.  A hit therefore shows up as t + inf failing
 // `t < max_range`: one exit test per step, and which exit it was is decided once, after the loop.
-template <bool COUNT>
+//
+// PADDED: the marcher's copy of the field is surrounded by P.pad cells of NaN.  Every sample of the loop
+// is taken at a parameter t < max_range from a pose inside the map, i.e. at most max_range (+1 for the
+// truncation, + TAIL_AHEAD for the look-ahead touch) cells outside it -- inside the padding.  Leaving the
+// map then needs no test of its own: t + NaN = NaN fails `t < max_range` like a hit does, and NaN != +inf
+// sorts it with the misses afterwards.  Three more instructions gone from every step (two ISETP, one BRA).
+template <bool COUNT, bool PADDED>
 __device__ __forceinline__ float march_ray(const MarchParams &P, float x0, float y0, float dx,
                                            float dy, uint32_t &steps, const FirstSample &f0)
 {
@@ -81,8 +87,8 @@ __device__ __forceinline__ float march_ray(const MarchParams &P, float x0, float
     for (;;) {
         px = __float2int_rz(fmaf(dx, t, x0));
         py = __float2int_rz(fmaf(dy, t, y0));
-        if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) { s = 0.0f; break; }   // left the map: a miss
-        s = __ldg(P.dist + (px * P.cols + py));
+        if (!PADDED && ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols)) { s = 0.0f; break; }   // left the map: a miss
+        s = __ldg(P.dist + (px * P.stride + py));
         if (COUNT) ++steps;
         t = __fadd_rn(t, s);
         if (!(t < P.max_range)) break;
@@ -97,19 +103,19 @@ __device__ __forceinline__ float march_ray(const MarchParams &P, float x0, float
             const float fx = fmaf(dx, t, x0), fy = fmaf(dy, t, y0);                                \
             px = __float2int_rz(fx);                                                               \
             py = __float2int_rz(fy);                                                               \
-            if ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols) { inside = false; break; } \
-            s = __ldg(P.dist + (px * P.cols + py));                                                \
+            if (!PADDED && ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols)) { inside = false; break; } \
+            s = __ldg(P.dist + (px * P.stride + py));                                              \
             if (COUNT) ++steps;                                                                    \
             const int ax = __float2int_rz(__fadd_rn(fx, adx)), ay = __float2int_rz(__fadd_rn(fy, ady)); \
             keep = __fadd_rn(keep, J);                                                             \
-            if ((unsigned)ax < (unsigned)P.rows && (unsigned)ay < (unsigned)P.cols)                \
-                asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(J) : "l"(P.dist + (ax * P.cols + ay))); \
+            if (PADDED || ((unsigned)ax < (unsigned)P.rows && (unsigned)ay < (unsigned)P.cols))    \
+                asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(J) : "l"(P.dist + (ax * P.stride + ay))); \
             t = __fadd_rn(t, s);                                                                   \
             if (!(t < P.max_range)) break;                                                         \
         }
         for (;;) { RL_TAIL_STEP(j0) RL_TAIL_STEP(j1) RL_TAIL_STEP(j2) RL_TAIL_STEP(j3) }
 #undef RL_TAIL_STEP
-        // the touched values (>= 1 or +inf) never influence the result; the test only keeps the loads alive
+        // the touched values (>= 1, +inf or NaN) never influence the result; the test only keeps the loads alive
         if (__fadd_rn(__fadd_rn(keep, j0), __fadd_rn(j1, __fadd_rn(j2, j3))) < 0.0f) return -1.0f;
         if (!inside) return P.max_range;
     }

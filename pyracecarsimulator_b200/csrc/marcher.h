@@ -10,6 +10,8 @@ struct rl_marcher {
     rl::MarchParams P{};
     uint32_t flags = 0;
     int sm_count = 148;
+    float *d_field = nullptr;    // this marcher's NaN-padded copy of the map's march field (P.pad > 0), or null
+    size_t field_bytes = 0;
     // host-variant staging (guarded by mu)
     std::mutex mu;
     cudaStream_t stream = nullptr, stream2 = nullptr;   // double-buffered H2D -> march -> D2H pipeline
@@ -55,7 +57,7 @@ cudaError_t launch_windowed(const rl_marcher *m, void (*kernel)(KArgs...), unsig
     unsigned n = 0;
     if (m->l2_window_bytes) {
         attr[n].id = cudaLaunchAttributeAccessPolicyWindow;
-        attr[n].val.accessPolicyWindow.base_ptr = const_cast<float *>(m->P.dist);
+        attr[n].val.accessPolicyWindow.base_ptr = const_cast<float *>(m->d_field ? m->d_field : m->P.dist);
         attr[n].val.accessPolicyWindow.num_bytes = m->l2_window_bytes;
         attr[n].val.accessPolicyWindow.hitRatio = m->l2_hit_ratio;
         attr[n].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;

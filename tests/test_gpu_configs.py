@@ -68,7 +68,7 @@ def test_config4_fused_rollout_full_size(orc, colombia, colombia_scan):
             poses[i] = s[:3]
         want = orc.car_is_crashed(m.calc_range_fan(poses, 1080, FOV), edge, 1080, steps, 0.001)
         agree += int(want == idx[c])
-    assert agree >= 47
+    assert agree == 48   # the f32 poses of all 65 536 cars equal the reference Car's (next test), so every index must agree
     print(f"config 4: {np.mean(idx >= 0) * 100:.1f}% of cars crash within {steps} steps")
 
 
@@ -103,8 +103,9 @@ def test_config4_crash_indices_vs_reference_car_all_cars(orc, colombia, colombia
     state_rel = float(np.max(np.abs(out["poses"].cpu().numpy().astype(np.float64) - ref_poses) / (np.abs(ref_poses) + 1e-12)))
     print(f"config 4 vs reference Car, all {n} cars: {pose_diff} of {n * steps} fp32 poses differ in any bit "
           f"(max relative difference {state_rel:.2e}); {idx_diff} crash indices differ")
-    assert idx_diff <= n // 1000, idx_diff          # quantified, and bounded at 0.1 %
-    assert pose_diff <= n * steps // 100, pose_diff
+    # measured on B200 (CUDA 12.9 libdevice): 0 of 3 276 800 poses differ in any bit, 0 crash indices differ
+    assert idx_diff == 0, idx_diff
+    assert pose_diff <= n * steps // 1000, pose_diff
 
 
 def test_config5_large_map_reduced_pose_count(orc):

@@ -176,6 +176,48 @@ def test_pipelined_inputs_produced_on_the_callers_stream_are_seen(big):
     assert L.rl_marcher_set_pipelined(rm._h, 7) == _native.RL_ERR_BAD_ARG
 
 
+# --------------------------------------------------------------------------- padded march field
+def test_padded_and_bounds_tested_marchers_agree(orc, big):
+    """The marcher's NaN-padded copy of the field removes the per-step bounds test; the bounds-tested kernels
+    (RL_FLAG_NO_PADDED_FIELD, or max_range > 2048 px) must give the same bits, also for rays that leave the map,
+    start on its edge, or head along it."""
+    import torch
+    rng = np.random.default_rng(4)
+    n = big["dist"].shape[0]
+    res, (ox, oy, _) = big["res"], big["origin"]
+    inner = maps.sample_free_poses(big["dist"], 3000, 55, res, big["origin"])
+    # poses hugging the border cells and just outside the map, every heading
+    edge = np.empty((2000, 3), np.float32)
+    side = rng.integers(0, 4, 2000)
+    along = rng.uniform(-2, n + 2, 2000)
+    off = rng.uniform(-1.5, 3.0, 2000)
+    col = np.where(side == 0, off, np.where(side == 1, n - off, along))
+    row = np.where(side == 2, off, np.where(side == 3, n - off, along))
+    edge[:, 0] = col * res + ox
+    edge[:, 1] = row * res + oy
+    edge[:, 2] = rng.uniform(-np.pi, np.pi, 2000)
+    poses = np.concatenate([inner, edge]).astype(np.float32)
+    want = orc.Marcher(big["dist"], 300, res, big["origin"]).calc_range_fan(poses, 61, FOV)
+    for flags, mr in ((0, 300), (_native.RL_FLAG_NO_PADDED_FIELD, 300)):
+        rm = range_libc.PyRayMarchingGPU(big["omap"], mr, flags=flags)
+        got = np.zeros(poses.shape[0] * 61, np.float32)
+        rm.calc_range_fan(poses, got, FOV, 61)
+        assert np.array_equal(got, want), flags
+        dp, do = torch.from_numpy(poses).cuda(), torch.zeros(poses.shape[0] * 61, dtype=torch.float32, device="cuda")
+        rm.calc_range_fan(dp, do, FOV, 61)
+        assert np.array_equal(do.cpu().numpy(), want)
+    # a range longer than the padding limit: bounds-tested kernels, compared with the oracle at that range
+    far = range_libc.PyRayMarchingGPU(big["omap"], 5000)
+    got = np.zeros(poses.shape[0] * 61, np.float32)
+    far.calc_range_fan(poses, got, FOV, 61)
+    assert np.array_equal(got, orc.Marcher(big["dist"], 5000, res, big["origin"]).calc_range_fan(poses, 61, FOV))
+    # fractional max_range
+    frac = range_libc.PyRayMarchingGPU(big["omap"], 123.75)
+    got = np.zeros(poses.shape[0] * 61, np.float32)
+    frac.calc_range_fan(poses, got, FOV, 61)
+    assert np.array_equal(got, orc.Marcher(big["dist"], 123.75, res, big["origin"]).calc_range_fan(poses, 61, FOV))
+
+
 # --------------------------------------------------------------------------- fused all-gather, repeat_angles + 16-byte stores
 @pytest.mark.parametrize("B,R", [(300, 60), (37, 61), (64, 1080)])
 def test_fused_allgather_repeat_angles_two_virtual_ranks(big, B, R):

@@ -1,7 +1,7 @@
 """Turn the ncu artefacts of a round into the tracked summaries under profiles/.
     python tools/make_profiles.py gpurun_out/r01_prof.ncu-rep gpurun_out/r01_launches.csv r01
-Writes profiles/<tag>_ncu_full_summary.md, profiles/<tag>_launches.csv + _launches_summary.md and
-profiles/traffic.json (DRAM bytes and warp instructions per launch of the march kernel, read by bench.py)."""
+Writes profiles/<tag>_ncu_full_summary.md and profiles/<tag>_launches.csv + _launches_summary.md.
+(profiles/traffic.json, which bench.py reads, comes from tools/make_traffic.py.)"""
 import collections
 import csv
 import json
@@ -28,8 +28,8 @@ want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio']
 cols = ['kernel'] + [w for w in want if w in idx]
 out = [f"# {tag} - ncu `--set full --clock-control none` summary (one row per captured launch)", "",
-       "Command: `ncu --set full --clock-control none --import-source on -k regex:\"march_pose|edt_\" -c 8 python bench.py "
-       "--steps 3 --warmup 3 --no-cpu-baseline` (B200, one GPU; times under ncu are cold-cache and serialised: compare "
+       "Command: `ncu --set full --clock-control none --import-source on -k regex:march_pose_kernel -s 6 -c 2 python bench.py "
+       "--steps 4 --warmup 3 --no-cpu-baseline --no-configs` (B200, one GPU; times under ncu are cold-cache and serialised: compare "
        "shares, not absolutes).", "", '| ' + ' | '.join(cols) + ' |', '|' + '---|' * len(cols)]
 
 
@@ -45,12 +45,6 @@ for r in data:
     if 'march_pose' in name:
         march.append((num(r, 'dram__bytes_read.sum') + num(r, 'dram__bytes_write.sum'), num(r, 'smsp__inst_executed.sum')))
 open(f'profiles/{tag}_ncu_full_summary.md', 'w').write('\n'.join(out) + '\n')
-if march:
-    json.dump({"kernel": "march_pose_kernel<FAN>", "dram_bytes_per_launch": sum(m[0] for m in march) / len(march),
-               "warp_insts_per_launch": sum(m[1] for m in march) / len(march), "launches": len(march),
-               "source": f"profiles/{tag}_ncu_full_summary.md (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum, "
-                         "smsp__inst_executed.sum)"}, open('profiles/traffic.json', 'w'), indent=1)
-
 shutil.copy(launches, f'profiles/{tag}_launches.csv')
 lr = [r for r in csv.reader(open(launches)) if r and r[0].isdigit()]
 agg = collections.OrderedDict()
@@ -64,10 +58,11 @@ for r, n in zip(lr, names):
         n += ' [e2e: zero-copy stores into pinned host memory]'
     agg.setdefault(n, []).append(float(r[-1]))
 tot = sum(sum(v) for v in agg.values())
-lines = [f"# {tag} - launch list of `python bench.py --steps 5 --warmup 3 --no-cpu-baseline` (ncu gpu__time_duration.sum, "
+lines = [f"# {tag} - launch list of `python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-configs` (ncu gpu__time_duration.sum, "
          "--clock-control none)", "", f"Raw: profiles/{tag}_launches.csv. Times are cold-cache and serialised under ncu: "
          "compare shares.  The fill kernel is bench.py's L2 flush, gather_kernel the roofline calibration (both outside "
-         "the timed step); march_pose_kernel<...,1,...> with COUNT is the step-counting pass; the march launches marked "
+         "the timed step; sector_kernel is the L2 full-sector calibration); march_pose_kernel<1, 1, ...> with COUNT is the step-counting "
+         "pass; most plain march launches belong to the steady-state section (3 modes x 3 repetitions x K launches, warm L2); the march launches marked "
          "[e2e] are the end-to-end scanMany calls, whose ranges are stored by the kernel straight into the caller's "
          "page-locked host buffer (PCIe-bound); march_crash_kernel is the fused checkCollisionMany figure.", "", "| kernel | launches | mean us | total us | share |",
          "|---|---|---|---|---|"]
