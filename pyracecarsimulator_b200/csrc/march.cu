@@ -349,42 +349,53 @@ int32_t host_pipeline(rl_marcher *m, const float *ins, int64_t in_stride_floats,
             m->cap_hout = (size_t)c * out_floats;
         }
         float *dst = out_pinned ? outs + b * out_floats : m->h_out;
-        // A few equal sub-chunks of >= 512K ranges (RL_HOST_SUBCHUNKS overrides the count, for
-        // experiments): every async call costs microseconds of host time, so the pipeline is kept
-        // shallow; small inputs (the fan's 12 B/pose) go up in one copy.
+        // Sub-chunks of >= 512K ranges (at most 4: every sub-chunk costs ~12 us of host API time and a few us of
+        // cross-stream latency, measured in profiles/r02_e2e_probe.txt; RL_HOST_SUBCHUNKS overrides the count).
+        // Kernels go back to back on the compute stream, the copies back to back on the copy stream, each
+        // waiting only for its own kernel's event: once the first sub-chunk is marched the PCIe link never
+        // idles.  (Kernel and copy of a sub-chunk on ONE stream, alternating between two streams -- the round-1
+        // scheme -- queues kernel i+2 behind copy i and leaves the link idle while it runs.)  For buffers from
+        // cudaHostAlloc the zero-copy stores above remain faster (368 vs 389 us for 17.7 MB); this path serves
+        // pageable buffers and buffers page-locked after the fact (1783 -> 1487 us and 415 -> 404 us per call).
         int64_t bounds[33];
         int64_t want = (c * out_floats) >> 19;
-        want = want < 1 ? 1 : (want > 4 ? 4 : want);   // measured best on PCIe Gen5 (tools/e2e_probe.py)
+        want = want < 1 ? 1 : (want > 4 ? 4 : want);
         if (const char *e = std::getenv("RL_HOST_SUBCHUNKS")) { const long v = std::atol(e); if (v >= 1 && v <= 32) want = v; }
         if (want > c) want = c;
         const int nsub = (int)want;
         for (int i = 0; i <= nsub; ++i) bounds[i] = c * i / nsub;
-        const bool one_h2d = (size_t)c * in_floats * sizeof(float) <= ((size_t)1 << 20);
-        cudaEvent_t up = nullptr;
-        if (one_h2d) {
-            RL_CUDA(cudaMemcpyAsync(m->d_in, src, (size_t)c * in_floats * sizeof(float), cudaMemcpyHostToDevice, st[0]));
-            if (nsub > 1) {
-                RL_CUDA(cudaEventCreateWithFlags(&up, cudaEventDisableTiming));
-                RL_CUDA(cudaEventRecord(up, st[0]));
-                RL_CUDA(cudaStreamWaitEvent(st[1], up, 0));
-            }
+        for (int i = 0; i < nsub; ++i) {
+            if (!m->sub_ev[i]) RL_CUDA(cudaEventCreateWithFlags(&m->sub_ev[i], cudaEventDisableTiming));
+            if (!out_pinned && !m->sub_done[i]) RL_CUDA(cudaEventCreateWithFlags(&m->sub_done[i], cudaEventDisableTiming));
         }
+        const bool one_h2d = (size_t)c * in_floats * sizeof(float) <= ((size_t)1 << 20);
+        cudaStream_t compute = st[0], copy = st[1];
+        if (one_h2d)
+            RL_CUDA(cudaMemcpyAsync(m->d_in, src, (size_t)c * in_floats * sizeof(float), cudaMemcpyHostToDevice, compute));
         for (int i = 0; i < nsub; ++i) {
             const int64_t u = bounds[i], n = bounds[i + 1] - bounds[i];
             if (n <= 0) continue;
-            cudaStream_t s = st[i & 1];
             if (!one_h2d)
                 RL_CUDA(cudaMemcpyAsync(m->d_in + u * in_floats, src + u * in_floats, (size_t)n * in_floats * sizeof(float),
-                                        cudaMemcpyHostToDevice, s));
-            rc = launch(u, n, m->d_in + u * in_floats, m->d_out + u * out_floats, s);
-            if (rc != RL_OK) { if (up) cudaEventDestroy(up); return rc; }
+                                        cudaMemcpyHostToDevice, compute));
+            rc = launch(u, n, m->d_in + u * in_floats, m->d_out + u * out_floats, compute);
+            if (rc != RL_OK) return rc;
+            RL_CUDA(cudaEventRecord(m->sub_ev[i], compute));
+            RL_CUDA(cudaStreamWaitEvent(copy, m->sub_ev[i], 0));
             RL_CUDA(cudaMemcpyAsync(dst + u * out_floats, m->d_out + u * out_floats, (size_t)n * out_floats * sizeof(float),
-                                    cudaMemcpyDeviceToHost, s));
+                                    cudaMemcpyDeviceToHost, copy));
+            if (!out_pinned) RL_CUDA(cudaEventRecord(m->sub_done[i], copy));
         }
-        if (up) cudaEventDestroy(up);
-        RL_CUDA(cudaStreamSynchronize(st[0]));
-        RL_CUDA(cudaStreamSynchronize(st[1]));
-        if (!out_pinned) std::memcpy(outs + b * out_floats, m->h_out, (size_t)c * out_floats * sizeof(float));
+        if (!out_pinned) {   // pageable caller buffer: unstage each sub-chunk as soon as it has landed
+            for (int i = 0; i < nsub; ++i) {
+                const int64_t u = bounds[i], n = bounds[i + 1] - bounds[i];
+                if (n <= 0) continue;
+                RL_CUDA(cudaEventSynchronize(m->sub_done[i]));
+                std::memcpy(outs + (b + u) * out_floats, m->h_out + u * out_floats, (size_t)n * out_floats * sizeof(float));
+            }
+        }
+        RL_CUDA(cudaStreamSynchronize(copy));
+        RL_CUDA(cudaStreamSynchronize(compute));
     }
     return RL_OK;
 }
@@ -513,6 +524,10 @@ int32_t rl_marcher_destroy(rl_marcher *m)
         }
         cudaFreeHost(m->h_in); cudaFreeHost(m->h_out);
         cudaFree(m->d_in); cudaFree(m->d_out); cudaFree(m->d_angles); cudaFree(m->d_steps); cudaFree(m->d_field);
+        for (int i = 0; i < 32; ++i) {
+            if (m->sub_ev[i]) cudaEventDestroy(m->sub_ev[i]);
+            if (m->sub_done[i]) cudaEventDestroy(m->sub_done[i]);
+        }
         if (m->l2_limit_raised) {
             std::lock_guard<std::mutex> lock(g_l2_mu);
             L2Carve &cv = g_l2[m->map->device];

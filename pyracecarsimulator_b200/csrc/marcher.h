@@ -17,6 +17,7 @@ struct rl_marcher {
     cudaStream_t stream = nullptr, stream2 = nullptr;   // double-buffered H2D -> march -> D2H pipeline
     float *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr, *d_angles = nullptr;
     size_t cap_in = 0, cap_out = 0, cap_hout = 0, cap_angles = 0;  // floats
+    cudaEvent_t sub_ev[32] = {}, sub_done[32] = {};   // per sub-chunk: kernel finished / copy landed (created on first use)
     // L2 persistence: the distance field is the one buffer every ray of every call re-reads, so each march
     // launch carries an access-policy window over it (persisting hits) and it stays L2-resident between
     // calls whatever else streams through the cache (0 = window unavailable / RL_FLAG_NO_L2_WINDOW)

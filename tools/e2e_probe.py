@@ -60,7 +60,7 @@ def child():
               f"then {t_rest:.0f} us per call = {P * B / t_rest / 1e3:.2f} Grays/s; registration disabled: {t_staged:.0f} us per call "
               f"= {P * B / t_staged / 1e3:.2f} Grays/s")
         return
-    print(f"subchunks={os.environ.get('RL_HOST_SUBCHUNKS', 'default')}: scanMany {t_sim:.0f} us, raw API {t_api:.0f} us, "
+    print(f"zerocopy={os.environ.get('RL_HOST_ZEROCOPY', '1')} subchunks={os.environ.get('RL_HOST_SUBCHUNKS', 'default')}: scanMany {t_sim:.0f} us, raw API {t_api:.0f} us, "
           f"bare pinned D2H {t_d2h:.0f} us, kernel {t_k:.0f} us -> e2e {P * B / t_sim / 1e3:.2f} Grays/s")
 
 
@@ -70,6 +70,11 @@ if __name__ == "__main__":
     elif len(sys.argv) > 1 and sys.argv[1] == "pageable":
         subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=dict(os.environ, RL_PROBE_PAGEABLE="1"))
     else:
-        for n in ("1", "2", "3", "4", "6", "8", "12"):
-            env = dict(os.environ, RL_HOST_SUBCHUNKS=n)
+        env = dict(os.environ, RL_HOST_ZEROCOPY="1")
+        env.pop("RL_HOST_SUBCHUNKS", None)
+        print("zero-copy stores (kernel writes the pinned host buffer):", flush=True)
+        subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env)
+        print("copy-engine pipeline (RL_HOST_ZEROCOPY=0), by sub-chunk count:", flush=True)
+        for n in ("1", "2", "4", "6", "8", "12", "16", "24"):
+            env = dict(os.environ, RL_HOST_SUBCHUNKS=n, RL_HOST_ZEROCOPY="0")
             subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env)
