@@ -576,6 +576,14 @@ def run_native(args, rank, world, local_rank):
                                             "note": "random 4-byte gathers (1 useful word per fetched sector): the sector rate "
                                                     "an L1-missing scalar gather reaches; NOT a ceiling for the march, whose "
                                                     "warps share sectors and hit L1 (round 1 reported achieved/this = 1.42)"}}
+        st_ms = steady_ms[1]
+        roofline["at_steady_state"] = {
+            "ms_per_launch": st_ms,
+            "l2_frac": None if not lts_sectors else lts_sectors / (st_ms * 1e-3) / (sector_gps * 1e9),
+            "issue_frac": None if not (warp_insts and issue_peak) else warp_insts / (st_ms * 1e-3) / issue_peak,
+            "achieved_algorithmic_gbs": alg_bytes / (st_ms * 1e-3) / 1e9,
+            "note": "the same per-launch traffic and instruction counts over the steady-state time per launch (consecutive "
+                    "launches overlapped, `steady_state`): what the kernel sustains when scans are issued back to back"}
         if dist_on:
             recv = (world - 1) * n_rays * 4.0
             roofline["nvlink"] = {"bytes_received_per_gpu_per_step": recv, "step_ms": ms_p2p / K,
