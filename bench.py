@@ -890,14 +890,16 @@ def config5(c):
     poses = maps.sample_free_poses(dist, mine, 505 + 31 * c.rank, y.resolution, y.origin)
     del dist
     d_p = torch.from_numpy(poses).to(c.dev)
-    chunk = min(per, 1 << 18)                 # 262 144 poses x 270 beams x 4 B = 283 MB per rank and piece
+    chunk = min(per, 1 << 18)                 # gathered pieces: 262 144 poses x 270 beams x 4 B = 283 MB per rank and piece
     n_chunks = -(-per // chunk)
+    chunk_s = min(per, 1 << 21)               # sharded pieces: 2 M poses (2.2 GB of ranges), two alternating buffers
+    n_chunks_s = -(-per // chunk_s)
     sp = int(torch.cuda.current_stream(c.local_rank).cuda_stream)
-    ring = [torch.empty(chunk * R, dtype=torch.float32, device=c.dev) for _ in range(2)]
+    ring = [torch.empty(chunk_s * R, dtype=torch.float32, device=c.dev) for _ in range(2)]
 
     def sharded():
-        for k in range(n_chunks):
-            a, b = min(k * chunk, mine), min((k + 1) * chunk, mine)
+        for k in range(n_chunks_s):
+            a, b = min(k * chunk_s, mine), min((k + 1) * chunk_s, mine)
             if b > a:
                 rm.calc_range_fan(d_p[a:b], ring[k & 1], FOV, R)
 
@@ -909,11 +911,13 @@ def config5(c):
     rays = n_total * R
     alg = 4.0 * msteps + 4.0 * rays + 12.0 * n_total
     res = {"workload": f"synth_map({n_map},{seed}) (256 MiB fp32 field, replicated), 16M poses x 270 beams sharded x{c.world}, "
-                       f"marched in {n_chunks} pieces of {chunk} poses per rank",
+                       f"marched in {n_chunks_s} pieces of {chunk_s} poses per rank, each piece visited in map order (64 px bins: the "
+                       "field is twice the L2, so the poses in flight are made to share their neighbourhoods)",
            "rays": rays, "kernel_ms": ms, "rays_per_s": rays / (ms * 1e-3), "march_steps_per_ray": msteps / rays,
            "algorithmic_bytes": alg, "achieved_gbs": alg / c.world / (ms * 1e-3) / 1e9,
            "frac_hbm": alg / c.world / (ms * 1e-3) / 1e9 / c.hbm_peak, "ingest_ms": omap.ingest_ms,
-           "bound": "the one HBM-side case: the field is twice the L2, misses are 32-byte sector gathers from HBM"}
+           "bound": "the one HBM-side case: the field is twice the L2, misses are 32-byte sector gathers from HBM (3.3 TB/s of "
+                    "them in caller order, profiles/r02_cfg35_metrics.csv; map order turns most into L2 hits)"}
     if c.dist_on:
         peer = PeerGather(c.local_rank, chunk * R, nbuf=2)
 

@@ -21,6 +21,7 @@ RL_ERR_OOM = -4
 RL_FLAG_DEFAULT = 0
 RL_FLAG_NO_L2_WINDOW = 1
 RL_FLAG_NO_PADDED_FIELD = 2
+RL_FLAG_NO_POSE_SORT = 4
 RL_PIPELINE_OFF, RL_PIPELINE_STREAMS, RL_PIPELINE_PDL = 0, 1, 2
 RL_DIST2_INF = 0x3FFFFFFF
 

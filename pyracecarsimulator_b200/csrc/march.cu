@@ -8,6 +8,8 @@
 #include <new>
 #include <utility>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "glibc_trig.cuh"
 #include "march.cuh"
 #include "marcher.h"
@@ -107,7 +109,8 @@ __device__ __forceinline__ void peer_store4(const PeerOut &peers, int64_t i, flo
 template <bool FAN, bool COUNT, bool SMALL, int OUT, bool PADDED>
 __global__ void __launch_bounds__(CTA_THREADS)
 march_pose_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_stride_floats,
-                  const float *__restrict__ angles, float *__restrict__ outs, int64_t num_rays_total,
+                  const float *__restrict__ angles, const uint32_t *__restrict__ perm,
+                  float *__restrict__ outs, int64_t num_rays_total,
                   int num_beams, rl::FastDiv div, float fov, float inc, unsigned long long *counter,
                   PeerOut peers)
 {
@@ -126,6 +129,12 @@ march_pose_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_s
             k = i / num_beams;
             j = (int)(i - k * num_beams);
         }
+        // perm: poses are visited in map order (sort_poses below) but read and written at their own index
+        int64_t io = i;
+        if (perm) {
+            k = __ldg(perm + k);
+            io = k * num_beams + j;
+        }
         const float *p = poses + k * pose_stride_floats;
         const float thw = __ldg(p + 2);
         const GridPose g = rl::world_to_grid(P.w, __ldg(p), __ldg(p + 1), thw);
@@ -136,9 +145,9 @@ march_pose_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_s
         float s, c;
         rl::glibc_sincosf(thg, &s, &c);
         const float r = __fmul_rn(rl::march_ray<COUNT, PADDED>(P, g.y, g.x, c, s, steps, f0), P.w.scale);
-        if (OUT == OUT_PEERS) peer_store(peers, i, r);
+        if (OUT == OUT_PEERS) peer_store(peers, io, r);
         else if (OUT == OUT_PEERS4) stage[threadIdx.x] = r;
-        else outs[i] = r;
+        else outs[io] = r;
     }
     if (OUT == OUT_PEERS4) {   // peers.offset is a multiple of 4 floats (checked by the host), so is the CTA's base
         __syncthreads();
@@ -166,6 +175,27 @@ pad_field_kernel(const float *__restrict__ src, int rows, int cols, int pad, flo
     const int r = (int)(i / stride) - pad, c = (int)(i % stride) - pad;
     dst[i] = ((unsigned)r < (unsigned)rows && (unsigned)c < (unsigned)cols) ? src[(size_t)r * cols + c]
                                                                             : __int_as_float(0x7fc00000);
+}
+
+// Map order for large fields.  When the field does not fit L2 (BASELINE config 5: 256 MiB, twice the L2) and the
+// poses arrive in random order, every CTA drags a different 600 x 600 px neighbourhood through L2: ncu shows a 32 %
+// L2 hit rate on the field loads and 3.3 TB/s of DRAM sector gathers.  Visiting the poses bin by bin (64 x 64 px
+// bins, row-major) keeps the neighbourhoods of the few thousand poses in flight inside a few MB.  The kernel
+// still reads pose k and writes its ranges at k * num_beams: only the ORDER of the work changes, not a bit of it.
+constexpr int SORT_BIN_SHIFT = 6;
+
+__global__ void __launch_bounds__(256)
+pose_bin_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_stride_floats, int64_t n,
+                int bins_per_row, uint32_t *__restrict__ keys, uint32_t *__restrict__ idx)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float *p = poses + k * pose_stride_floats;
+    const GridPose g = rl::world_to_grid(P.w, __ldg(p), __ldg(p + 1), 0.0f);
+    // saturating conversions; NaN -> 0: any key is fine, the order is only a cache hint
+    const int row = min(max(__float2int_rz(g.y), 0), P.rows - 1), col = min(max(__float2int_rz(g.x), 0), P.cols - 1);
+    keys[k] = (uint32_t)((row >> SORT_BIN_SHIFT) * bins_per_row + (col >> SORT_BIN_SHIFT));
+    idx[k] = (uint32_t)k;
 }
 
 // Ranges that already exist on this GPU -> slot `rank` of every GPU's gathered buffer (16-byte stores).  The
@@ -274,9 +304,31 @@ int32_t launch_pose(rl_marcher *m, const float *d_poses, int64_t stride_rows, co
     unsigned long long *ctr = m->count ? m->d_steps : nullptr;
     const int64_t stride_floats = stride_rows * 3;
     const PeerOut po = peers ? *peers : PeerOut{};
+    // poses in map order when the field is too large for L2 (see pose_bin_kernel); scratch is stream-ordered
+    const uint32_t *d_perm = nullptr;
+    void *scratch = nullptr;
+    if (m->sort_poses && !peers && num_poses >= m->sort_min_poses && num_poses < ((int64_t)1 << 31)) {
+        const int bins_per_row = (m->P.cols >> SORT_BIN_SHIFT) + 1, bin_rows = (m->P.rows >> SORT_BIN_SHIFT) + 1;
+        int bits = 1;
+        while (((int64_t)1 << bits) < (int64_t)bins_per_row * bin_rows) ++bits;
+        size_t temp_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                        (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)num_poses, 0, bits, s);
+        const size_t n4 = ((size_t)num_poses * sizeof(uint32_t) + 255) & ~(size_t)255;
+        if (cudaMallocAsync(&scratch, 4 * n4 + temp_bytes, s) == cudaSuccess) {
+            uint32_t *keys = static_cast<uint32_t *>(scratch), *idx = keys + n4 / 4, *keys2 = idx + n4 / 4, *perm = keys2 + n4 / 4;
+            pose_bin_kernel<<<(unsigned)((num_poses + 255) / 256), 256, 0, s>>>(m->P, d_poses, stride_floats, num_poses,
+                                                                                  bins_per_row, keys, idx);
+            cub::DeviceRadixSort::SortPairs(perm + n4 / 4, temp_bytes, keys, keys2, idx, perm, (int)num_poses, 0, bits, s);
+            d_perm = perm;
+        } else {
+            cudaGetLastError();   // no scratch: march in the caller's order
+            scratch = nullptr;
+        }
+    }
 #define RL_LAUNCH2(COUNT, SMALL, OUT, PADDED)                                                      \
     RL_CUDA(launch_windowed(m, march_pose_kernel<FAN, COUNT, SMALL, OUT, PADDED>, (unsigned)blocks, s, pdl, m->P, d_poses, \
-                            stride_floats, d_angles, d_outs, total, num_beams, div, fov, inc, ctr, po))
+                            stride_floats, d_angles, d_perm, d_outs, total, num_beams, div, fov, inc, ctr, po))
 #define RL_LAUNCH(COUNT, SMALL, OUT)                                                               \
     do { if (m->P.pad > 0) RL_LAUNCH2(COUNT, SMALL, OUT, true); else RL_LAUNCH2(COUNT, SMALL, OUT, false); } while (0)
     if (peers) {
@@ -292,6 +344,7 @@ int32_t launch_pose(rl_marcher *m, const float *d_poses, int64_t stride_rows, co
     }
 #undef RL_LAUNCH2
 #undef RL_LAUNCH
+    if (scratch) cudaFreeAsync(scratch, s);
     RL_CUDA(cudaGetLastError());
     return RL_OK;
 }
@@ -436,7 +489,7 @@ int32_t rl_marcher_create(const rl_map *map, float max_range_px, uint32_t flags,
 {
     if (!map || !out) return rl::fail(RL_ERR_BAD_ARG, "rl_marcher_create: null pointer");
     if (!(max_range_px > 0.0f)) return rl::fail(RL_ERR_BAD_ARG, "rl_marcher_create: max_range_px must be > 0");
-    if (flags & ~(uint32_t)(RL_FLAG_NO_L2_WINDOW | RL_FLAG_NO_PADDED_FIELD)) return rl::fail(RL_ERR_BAD_ARG, "rl_marcher_create: unknown flag");
+    if (flags & ~(uint32_t)(RL_FLAG_NO_L2_WINDOW | RL_FLAG_NO_PADDED_FIELD | RL_FLAG_NO_POSE_SORT)) return rl::fail(RL_ERR_BAD_ARG, "rl_marcher_create: unknown flag");
     rl::DeviceGuard guard(map->device);
     if (!guard.ok) return rl::fail(RL_ERR_CUDA, "rl_marcher_create: cudaSetDevice failed");
     rl_marcher *m = new (std::nothrow) rl_marcher();
@@ -497,6 +550,13 @@ int32_t rl_marcher_create(const rl_map *map, float max_range_px, uint32_t flags,
             }
         }
         cudaGetLastError();
+    }
+    {   // poses are visited in map order when the field cannot live in L2 (RL_SORT_POSES=0/1 overrides, for measurements)
+        int l2_bytes = 0;
+        cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, map->device);
+        const size_t field = m->field_bytes ? m->field_bytes : (size_t)map->rows * map->cols * sizeof(float);
+        m->sort_poses = !(flags & RL_FLAG_NO_POSE_SORT) && m->l2_window_bytes == 0 && field > (size_t)l2_bytes;
+        if (const char *e = std::getenv("RL_SORT_POSES")) m->sort_poses = e[0] == '1' && !(flags & RL_FLAG_NO_POSE_SORT);
     }
     cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking);

@@ -12,6 +12,8 @@ struct rl_marcher {
     int sm_count = 148;
     float *d_field = nullptr;    // this marcher's NaN-padded copy of the map's march field (P.pad > 0), or null
     size_t field_bytes = 0;
+    bool sort_poses = false;      // field larger than L2: large batches are marched in map order (march.cu: pose_bin_kernel)
+    int64_t sort_min_poses = 16384;
     // host-variant staging (guarded by mu)
     std::mutex mu;
     cudaStream_t stream = nullptr, stream2 = nullptr;   // double-buffered H2D -> march -> D2H pipeline

@@ -218,6 +218,46 @@ def test_padded_and_bounds_tested_marchers_agree(orc, big):
     assert np.array_equal(got, orc.Marcher(big["dist"], 123.75, res, big["origin"]).calc_range_fan(poses, 61, FOV))
 
 
+def test_map_order_marching_is_invisible(big):
+    """Fields larger than L2 are marched in map order (a radix sort of pose indices per call); forced here on a
+    small map: every entry point must return exactly what the caller-order march returns, at the caller's indices."""
+    import torch
+    n, R = 20000, 33
+    poses = maps.sample_free_poses(big["dist"], n, 808, big["res"], big["origin"])
+    poses[::997, 0] = np.nan                       # poses that convert to no cell at all
+    poses[5::991, 1] = 1e30
+    plain = range_libc.PyRayMarchingGPU(big["omap"], 300, flags=_native.RL_FLAG_NO_POSE_SORT)
+    os.environ["RL_SORT_POSES"] = "1"
+    try:
+        srt = range_libc.PyRayMarchingGPU(big["omap"], 300)
+    finally:
+        os.environ.pop("RL_SORT_POSES", None)
+    dp = torch.from_numpy(poses).cuda()
+    a, b = (torch.zeros(n * R, dtype=torch.float32, device="cuda") for _ in range(2))
+    plain.calc_range_fan(dp, a, FOV, R)
+    srt.calc_range_fan(dp, b, FOV, R)
+    assert torch.equal(a, b)
+    angles = torch.linspace(-2.0, 2.0, R, device="cuda")
+    plain.calc_range_repeat_angles(dp, angles, a)
+    srt.calc_range_repeat_angles(dp, angles, b)
+    assert torch.equal(a, b)
+    # host path and the fork's strided layout (pose k in row k * num_rays)
+    ha, hb = np.zeros(n * R, np.float32), np.zeros(n * R, np.float32)
+    plain.calc_range_fan(poses, ha, FOV, R)
+    srt.calc_range_fan(poses, hb, FOV, R)
+    assert np.array_equal(ha, hb)
+    ins = np.zeros((n * R, 3), np.float32)
+    ins[::R] = poses
+    hc = np.zeros(n * R, np.float32)
+    srt.calc_range_many(ins, hc, FOV, R)
+    assert np.array_equal(hc, ha)
+    srt.count_steps(True)
+    plain.count_steps(True)
+    srt.calc_range_fan(dp, b, FOV, R)
+    plain.calc_range_fan(dp, a, FOV, R)
+    assert srt.last_steps() == plain.last_steps() and torch.equal(a, b)
+
+
 # --------------------------------------------------------------------------- fused all-gather, repeat_angles + 16-byte stores
 @pytest.mark.parametrize("B,R", [(300, 60), (37, 61), (64, 1080)])
 def test_fused_allgather_repeat_angles_two_virtual_ranks(big, B, R):

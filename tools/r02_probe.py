@@ -166,8 +166,11 @@ def cfg():
     omap5 = range_libc.PyOMap(y5)
     os.unlink(path)
     dist5 = omap5.dist()
-    rm5 = range_libc.PyRayMarchingGPU(omap5, 300)
-    for n5 in (2_000_000,):
+    for sort in ("1", "0"):
+      os.environ["RL_SORT_POSES"] = sort
+      rm5 = range_libc.PyRayMarchingGPU(omap5, 300)
+      os.environ.pop("RL_SORT_POSES", None)
+      for n5 in (2_000_000,):
         b5 = 270
         poses5 = torch.from_numpy(maps.sample_free_poses(dist5, n5, 505, y5.resolution, y5.origin)).cuda()
         out5 = torch.empty(n5 * b5, dtype=torch.float32, device="cuda")
@@ -176,8 +179,13 @@ def cfg():
         rm5.calc_range_fan(poses5, out5, FOV, b5)
         steps = rm5.last_steps()
         rm5.count_steps(False)
-        print(json.dumps({"probe": "cfg5_share", "poses": n5, "ms": ms, "grays_per_s": n5 * b5 / ms / 1e6,
-                          "steps_per_ray": steps / (n5 * b5), "ingest_ms": omap5.ingest_ms}), flush=True)
+        chk = float(out5.double().sum().item())
+        print(json.dumps({"probe": "cfg5_share", "map_order": sort == "1", "poses": n5, "ms": ms, "grays_per_s": n5 * b5 / ms / 1e6,
+                          "steps_per_ray": steps / (n5 * b5), "ingest_ms": omap5.ingest_ms, "checksum": chk}), flush=True)
+        chunk = 1 << 18
+        ms = timeit(lambda: [rm5.calc_range_fan(poses5[a:a + chunk], out5[:chunk * b5], FOV, b5) for a in range(0, n5, chunk)])
+        print(json.dumps({"probe": "cfg5_share_in_pieces_of_262144", "map_order": sort == "1", "ms": ms,
+                          "grays_per_s": n5 * b5 / ms / 1e6}), flush=True)
 
 
 if __name__ == "__main__":
