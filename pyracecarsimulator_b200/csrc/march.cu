@@ -8,7 +8,7 @@
 #include <new>
 #include <utility>
 
-#include <cub/device/device_radix_sort.cuh>
+#include <cooperative_groups.h>
 
 #include "glibc_trig.cuh"
 #include "march.cuh"
@@ -19,6 +19,7 @@ namespace {
 using rl::GridPose;
 using rl::MarchParams;
 using rl::launch_windowed;
+using rl::launch_windowed_ex;
 
 constexpr int CTA_THREADS = rl::MARCH_CTA_THREADS;
 
@@ -106,11 +107,26 @@ __device__ __forceinline__ void peer_store4(const PeerOut &peers, int64_t i, flo
     }
 }
 
+// Beam j of the pose at `p` (x, y, theta in the world frame): the range in metres.
+template <bool FAN, bool COUNT, bool PADDED>
+__device__ __forceinline__ float pose_ray(const MarchParams &P, const float *__restrict__ p, const float *__restrict__ angles,
+                                          int j, float fov, float inc, uint32_t &steps)
+{
+    const float thw = __ldg(p + 2);
+    const GridPose g = rl::world_to_grid(P.w, __ldg(p), __ldg(p + 1), thw);
+    float thg;
+    if (FAN) thg = __fadd_rn(-__fadd_rn(thw, fmaf((float)j, inc, -0.5f * fov)), P.w.rotation_const);
+    else thg = __fsub_rn(g.theta, __ldg(angles + j));
+    const rl::FirstSample f0 = rl::first_sample(P, g.y, g.x);
+    float s, c;
+    rl::glibc_sincosf(thg, &s, &c);
+    return __fmul_rn(rl::march_ray<COUNT, PADDED>(P, g.y, g.x, c, s, steps, f0), P.w.scale);
+}
+
 template <bool FAN, bool COUNT, bool SMALL, int OUT, bool PADDED>
 __global__ void __launch_bounds__(CTA_THREADS)
 march_pose_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_stride_floats,
-                  const float *__restrict__ angles, const uint32_t *__restrict__ perm,
-                  float *__restrict__ outs, int64_t num_rays_total,
+                  const float *__restrict__ angles, float *__restrict__ outs, int64_t num_rays_total,
                   int num_beams, rl::FastDiv div, float fov, float inc, unsigned long long *counter,
                   PeerOut peers)
 {
@@ -129,25 +145,10 @@ march_pose_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_s
             k = i / num_beams;
             j = (int)(i - k * num_beams);
         }
-        // perm: poses are visited in map order (sort_poses below) but read and written at their own index
-        int64_t io = i;
-        if (perm) {
-            k = __ldg(perm + k);
-            io = k * num_beams + j;
-        }
-        const float *p = poses + k * pose_stride_floats;
-        const float thw = __ldg(p + 2);
-        const GridPose g = rl::world_to_grid(P.w, __ldg(p), __ldg(p + 1), thw);
-        float thg;
-        if (FAN) thg = __fadd_rn(-__fadd_rn(thw, fmaf((float)j, inc, -0.5f * fov)), P.w.rotation_const);
-        else thg = __fsub_rn(g.theta, __ldg(angles + j));
-        const rl::FirstSample f0 = rl::first_sample(P, g.y, g.x);
-        float s, c;
-        rl::glibc_sincosf(thg, &s, &c);
-        const float r = __fmul_rn(rl::march_ray<COUNT, PADDED>(P, g.y, g.x, c, s, steps, f0), P.w.scale);
-        if (OUT == OUT_PEERS) peer_store(peers, io, r);
+        const float r = pose_ray<FAN, COUNT, PADDED>(P, poses + k * pose_stride_floats, angles, j, fov, inc, steps);
+        if (OUT == OUT_PEERS) peer_store(peers, i, r);
         else if (OUT == OUT_PEERS4) stage[threadIdx.x] = r;
-        else outs[io] = r;
+        else outs[i] = r;
     }
     if (OUT == OUT_PEERS4) {   // peers.offset is a multiple of 4 floats (checked by the host), so is the CTA's base
         __syncthreads();
@@ -177,25 +178,217 @@ pad_field_kernel(const float *__restrict__ src, int rows, int cols, int pad, flo
                                                                             : __int_as_float(0x7fc00000);
 }
 
-// Map order for large fields.  When the field does not fit L2 (BASELINE config 5: 256 MiB, twice the L2) and the
-// poses arrive in random order, every CTA drags a different 600 x 600 px neighbourhood through L2: ncu shows a 32 %
-// L2 hit rate on the field loads and 3.3 TB/s of DRAM sector gathers.  Visiting the poses bin by bin (64 x 64 px
-// bins, row-major) keeps the neighbourhoods of the few thousand poses in flight inside a few MB.  The kernel
-// still reads pose k and writes its ranges at k * num_beams: only the ORDER of the work changes, not a bit of it.
-constexpr int SORT_BIN_SHIFT = 6;
+// ---- map order + SM territories for large batches ----
+// A batch of many poses (a particle set, a pose grid: BASELINE configs 3 and 5 hold one pose per four map cells)
+// samples every neighbourhood of the map hundreds of times, yet in the caller's order those samples are spread
+// over all SMs and over the whole launch, so nearly every one of them misses L1 (14 % hits on config 3) and the
+// kernel runs at the one-sector-per-clock rate at which an SM can send L1 misses to L2 (ncu:
+// l1tex__m_l1tex2xbar_req_cycles_active 77 %); with a field larger than L2 (config 5) they miss L2 as well (3.3 TB/s
+// of DRAM sector gathers).  Two launches turn that reuse into L1 hits:
+//   1. pose_sort_kernel, a counting sort in ONE cooperative launch, puts the poses' indices in MAP ORDER -- Morton
+//      order of their cells (16 px or larger, at most 2^16 of them): histogram, scan and scatter phases separated by
+//      grid-wide barriers (cub's radix sort: 72 us of kernels in 6 launches, 150 us with their launch gaps);
+//   2. march_territory_kernel cuts that order into one contiguous range per SM.  The warps resident on an SM claim 32-ray tasks from
+//      their SM's own range (one atomic per TERR_CLAIM tasks), so at any moment an SM works on a few dozen
+//      neighbouring poses and sweeps slowly through one compact territory of the map, whose field cells stay in its
+//      L1 (74 % hits on config 3, L2 sector reads down 3.2 x).  A warp whose range is used up helps out in the range
+//      with the most work left.
+// The kernel still reads pose k and writes its ranges at k * num_beams: only the ORDER of the work changes, not a
+// bit of any result (tests/test_gpu_round2.py::test_map_order_marching_is_invisible).
+namespace cg = cooperative_groups;
 
-__global__ void __launch_bounds__(256)
-pose_bin_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_stride_floats, int64_t n,
-                int bins_per_row, uint32_t *__restrict__ keys, uint32_t *__restrict__ idx)
+constexpr int TERR_CLAIM = 4;          // 32-ray tasks per atomic
+constexpr int TERR_CLAIM_STRIDE = 8;   // uint32 between the ranges' counters: one 32-byte sector each
+constexpr int SORT_MAX_SIDE_BITS = 8;  // at most 256 x 256 Morton cells: keys fit 16 bits
+constexpr int SORT_TILE = 32;          // bins scanned by one CTA in the scan phase
+
+__device__ __forceinline__ uint32_t spread_bits8(uint32_t v)   // abcdefgh -> 0a0b0c0d0e0f0g0h
 {
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const float *p = poses + k * pose_stride_floats;
-    const GridPose g = rl::world_to_grid(P.w, __ldg(p), __ldg(p + 1), 0.0f);
-    // saturating conversions; NaN -> 0: any key is fine, the order is only a cache hint
-    const int row = min(max(__float2int_rz(g.y), 0), P.rows - 1), col = min(max(__float2int_rz(g.x), 0), P.cols - 1);
-    keys[k] = (uint32_t)((row >> SORT_BIN_SHIFT) * bins_per_row + (col >> SORT_BIN_SHIFT));
-    idx[k] = (uint32_t)k;
+    v &= 0xffu;
+    v = (v | (v << 4)) & 0x0f0fu;
+    v = (v | (v << 2)) & 0x3333u;
+    v = (v | (v << 1)) & 0x5555u;
+    return v;
+}
+
+struct Territories {
+    // counting sort of the poses by map cell
+    uint16_t *keys;            // num_poses
+    uint32_t *cursor;          // n_bins: count -> exclusive offset inside the bin's tile -> scatter cursor (zeroed before the launch)
+    uint32_t *tile_off;        // n_bins / SORT_TILE: poses in all earlier tiles
+    uint32_t *perm;            // num_poses: pose indices in map order
+    uint32_t n_bins;           // 4^side_bits
+    int shift;                 // cell = (row >> shift, col >> shift)
+    int64_t num_poses;
+    // work distribution
+    uint32_t *claims;          // one counter per range (zeroed before the launch): tasks of the range handed out so far
+    uint32_t n_ranges;         // = SM count
+    uint32_t tasks_per_range;  // 32-ray tasks per range (the last range may be shorter)
+    uint32_t n_tasks;
+};
+
+__device__ __forceinline__ uint32_t territory_len(const Territories &T, uint32_t r)
+{
+    const uint64_t base = (uint64_t)r * T.tasks_per_range;
+    return base < T.n_tasks ? (uint32_t)min((uint64_t)T.tasks_per_range, (uint64_t)T.n_tasks - base) : 0u;
+}
+
+// The range with the most unclaimed tasks (all lanes get the same answer), or 0xffffffff when none is left.
+__device__ __forceinline__ uint32_t busiest_territory(const Territories &T, unsigned lane)
+{
+    uint32_t best_left = 0, best_r = 0xffffffffu;
+    for (uint32_t q = lane; q < T.n_ranges; q += 32) {
+        const uint32_t c = *reinterpret_cast<const volatile uint32_t *>(T.claims + q * TERR_CLAIM_STRIDE);
+        const uint32_t len = territory_len(T, q);
+        const uint32_t left = c < len ? len - c : 0u;
+        if (left > best_left) { best_left = left; best_r = q; }
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        const uint32_t ol = __shfl_xor_sync(0xffffffffu, best_left, off), orr = __shfl_xor_sync(0xffffffffu, best_r, off);
+        if (ol > best_left || (ol == best_left && orr < best_r)) { best_left = ol; best_r = orr; }
+    }
+    return best_left ? best_r : 0xffffffffu;
+}
+
+// One atomic per distinct key of the warp: a particle cloud puts a million poses into a few dozen cells, and
+// same-address atomics are served one after the other.  Returns this lane's rank among the warp's lanes with
+// its key plus the value the leader's atomic returned (valid for every lane of the group).
+template <bool WANT_POS>
+__device__ __forceinline__ uint32_t grouped_atomic_add(uint32_t *counters, uint32_t key, bool valid)
+{
+    const unsigned active = __ballot_sync(0xffffffffu, valid);
+    uint32_t pos = 0;
+    if (valid) {
+        const unsigned peers = __match_any_sync(active, key);
+        const int leader = __ffs(peers) - 1;
+        const unsigned lane = threadIdx.x & 31;
+        if (WANT_POS) {
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(counters + key, (uint32_t)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        } else if ((int)lane == leader) {
+            atomicAdd(counters + key, (uint32_t)__popc(peers));   // result unused: a fire-and-forget reduction
+        }
+    }
+    return pos;
+}
+
+__global__ void __launch_bounds__(CTA_THREADS)
+pose_sort_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_stride_floats, Territories T)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ uint32_t warp_sum[CTA_THREADS / 32];
+    const int64_t tid = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x, nthreads = (int64_t)gridDim.x * CTA_THREADS;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // 1. keys + histogram (whole warps iterate together: the grouped atomic is warp-synchronous)
+    for (int64_t k0 = tid - lane; k0 < T.num_poses; k0 += nthreads) {
+        const int64_t k = k0 + lane;
+        const bool valid = k < T.num_poses;
+        uint32_t key = 0;
+        if (valid) {
+            const float *p = poses + k * pose_stride_floats;
+            const GridPose g = rl::world_to_grid(P.w, __ldg(p), __ldg(p + 1), 0.0f);
+            // saturating conversions; NaN -> 0: any key is fine, the order is only a cache hint
+            const int row = min(max(__float2int_rz(g.y), 0), P.rows - 1), col = min(max(__float2int_rz(g.x), 0), P.cols - 1);
+            key = (spread_bits8((uint32_t)(row >> T.shift)) << 1) | spread_bits8((uint32_t)(col >> T.shift));
+            T.keys[k] = (uint16_t)key;
+        }
+        grouped_atomic_add<false>(T.cursor, key, valid);
+    }
+    grid.sync();
+    // 2a. every CTA scans one tile of SORT_TILE bins: count -> exclusive offset inside the tile; tile total -> tile_off
+    const uint32_t n_tiles = T.n_bins / SORT_TILE;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (warp == 0) {
+            const uint32_t c = T.cursor[tile * SORT_TILE + lane];
+            uint32_t inc = c;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, off);
+                if ((int)lane >= off) inc += o;
+            }
+            T.cursor[tile * SORT_TILE + lane] = inc - c;
+            if (lane == 31) T.tile_off[tile] = inc;
+        }
+    }
+    grid.sync();
+    // 2b. CTA 0 turns the tile totals into exclusive offsets
+    if (blockIdx.x == 0) {
+        uint32_t carry = 0;
+        for (uint32_t base = 0; base < n_tiles; base += CTA_THREADS) {
+            const uint32_t i = base + threadIdx.x;
+            const uint32_t c = i < n_tiles ? T.tile_off[i] : 0u;
+            uint32_t inc = c;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, off);
+                if ((int)lane >= off) inc += o;
+            }
+            if (lane == 31) warp_sum[warp] = inc;
+            __syncthreads();
+            uint32_t before = carry;
+            for (unsigned w = 0; w < warp; ++w) before += warp_sum[w];
+            if (i < n_tiles) T.tile_off[i] = before + inc - c;
+            for (unsigned w = 0; w < CTA_THREADS / 32; ++w) carry += warp_sum[w];
+            __syncthreads();
+        }
+    }
+    grid.sync();
+    // 3. scatter the pose indices to their cells' slots
+    for (int64_t k0 = tid - lane; k0 < T.num_poses; k0 += nthreads) {
+        const int64_t k = k0 + lane;
+        const bool valid = k < T.num_poses;
+        const uint32_t key = valid ? T.keys[k] : 0u;
+        const uint32_t pos = grouped_atomic_add<true>(T.cursor, key, valid);
+        if (valid) T.perm[T.tile_off[key / SORT_TILE] + pos] = (uint32_t)k;
+    }
+}
+
+template <bool FAN, bool COUNT, bool SMALL, bool PADDED>
+__global__ void __launch_bounds__(CTA_THREADS, 2048 / CTA_THREADS)   // 32 registers, like the plain kernel: every warp slot of the SM
+march_territory_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_stride_floats,
+                       const float *__restrict__ angles, float *__restrict__ outs, int64_t num_rays_total,
+                       int num_beams, rl::FastDiv div, float fov, float inc, unsigned long long *counter, Territories T)
+{
+    release_dependents();
+    const unsigned lane = threadIdx.x & 31;
+    uint32_t smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    uint32_t r = smid % T.n_ranges;
+    uint32_t steps = 0;
+    while (r != 0xffffffffu) {
+        const uint32_t len = territory_len(T, r);
+        uint32_t c = 0;
+        if (lane == 0) c = atomicAdd(T.claims + r * TERR_CLAIM_STRIDE, (uint32_t)TERR_CLAIM);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= len) {   // this range is used up: help where the most work is left
+            r = busiest_territory(T, lane);
+            continue;
+        }
+        const uint32_t first = r * T.tasks_per_range + c, last = first + min((uint32_t)TERR_CLAIM, len - c);
+#pragma unroll 1
+        for (uint32_t task = first; task < last; ++task) {
+            const int64_t i = (int64_t)task * 32 + lane;
+            if (i < num_rays_total) {
+                int64_t k;
+                int j;
+                if (SMALL) {
+                    const uint32_t k32 = rl::fast_div((uint32_t)i, div);
+                    k = k32;
+                    j = (int)((uint32_t)i - k32 * (uint32_t)num_beams);
+                } else {
+                    k = i / num_beams;
+                    j = (int)(i - k * num_beams);
+                }
+                k = __ldg(T.perm + k);
+                const float rng = pose_ray<FAN, COUNT, PADDED>(P, poses + k * pose_stride_floats, angles, j, fov, inc, steps);
+                __stcs(outs + (k * num_beams + j), rng);   // streaming store: the ranges are not read again here
+            }
+        }
+    }
+    flush_steps<COUNT>(steps, counter);
 }
 
 // Ranges that already exist on this GPU -> slot `rank` of every GPU's gathered buffer (16-byte stores).  The
@@ -304,31 +497,75 @@ int32_t launch_pose(rl_marcher *m, const float *d_poses, int64_t stride_rows, co
     unsigned long long *ctr = m->count ? m->d_steps : nullptr;
     const int64_t stride_floats = stride_rows * 3;
     const PeerOut po = peers ? *peers : PeerOut{};
-    // poses in map order when the field is too large for L2 (see pose_bin_kernel); scratch is stream-ordered
-    const uint32_t *d_perm = nullptr;
-    void *scratch = nullptr;
-    if (m->sort_poses && !peers && num_poses >= m->sort_min_poses && num_poses < ((int64_t)1 << 31)) {
-        const int bins_per_row = (m->P.cols >> SORT_BIN_SHIFT) + 1, bin_rows = (m->P.rows >> SORT_BIN_SHIFT) + 1;
-        int bits = 1;
-        while (((int64_t)1 << bits) < (int64_t)bins_per_row * bin_rows) ++bits;
-        size_t temp_bytes = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-                                        (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)num_poses, 0, bits, s);
-        const size_t n4 = ((size_t)num_poses * sizeof(uint32_t) + 255) & ~(size_t)255;
-        if (cudaMallocAsync(&scratch, 4 * n4 + temp_bytes, s) == cudaSuccess) {
-            uint32_t *keys = static_cast<uint32_t *>(scratch), *idx = keys + n4 / 4, *keys2 = idx + n4 / 4, *perm = keys2 + n4 / 4;
-            pose_bin_kernel<<<(unsigned)((num_poses + 255) / 256), 256, 0, s>>>(m->P, d_poses, stride_floats, num_poses,
-                                                                                  bins_per_row, keys, idx);
-            cub::DeviceRadixSort::SortPairs(perm + n4 / 4, temp_bytes, keys, keys2, idx, perm, (int)num_poses, 0, bits, s);
-            d_perm = perm;
-        } else {
-            cudaGetLastError();   // no scratch: march in the caller's order
-            scratch = nullptr;
+    // large batches are marched in map order, by SM territories (see march_territory_kernel); scratch is stream-ordered
+    if (m->sort_poses && !peers && num_poses >= m->sort_min_poses && num_poses < ((int64_t)1 << 32) &&
+        blocks * (CTA_THREADS / 32) < ((int64_t)1 << 32)) {
+        Territories terr{};
+        int side = m->P.rows > m->P.cols ? m->P.rows : m->P.cols, side_bits = 1;
+        terr.shift = m->sort_shift;
+        while (((side - 1) >> terr.shift) >= (1 << SORT_MAX_SIDE_BITS)) ++terr.shift;
+        while ((1 << side_bits) <= ((side - 1) >> terr.shift)) ++side_bits;
+        if (side_bits < 3) side_bits = 3;   // at least SORT_TILE * 2 bins
+        terr.n_bins = 1u << (2 * side_bits);
+        terr.num_poses = num_poses;
+        auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        const size_t keys_b = up((size_t)num_poses * sizeof(uint16_t)), perm_b = up((size_t)num_poses * sizeof(uint32_t)),
+                     tile_b = up((size_t)terr.n_bins / SORT_TILE * sizeof(uint32_t)),
+                     zero_b = up((size_t)terr.n_bins * sizeof(uint32_t)) + up((size_t)m->sm_count * TERR_CLAIM_STRIDE * sizeof(uint32_t));
+        void *scratch = nullptr;
+        // the marcher's own pool keeps the scratch between calls (the device's default pool hands its memory back to
+        // the driver at every synchronisation: 0.2 ms per call to get it again, measured)
+        if (m->scratch_pool && cudaMallocFromPoolAsync(&scratch, zero_b + keys_b + perm_b + tile_b, m->scratch_pool, s) == cudaSuccess) {
+            char *base = static_cast<char *>(scratch);
+            terr.cursor = reinterpret_cast<uint32_t *>(base);
+            terr.claims = reinterpret_cast<uint32_t *>(base + up((size_t)terr.n_bins * sizeof(uint32_t)));
+            terr.keys = reinterpret_cast<uint16_t *>(base + zero_b);
+            terr.perm = reinterpret_cast<uint32_t *>(base + zero_b + keys_b);
+            terr.tile_off = reinterpret_cast<uint32_t *>(base + zero_b + keys_b + perm_b);
+            terr.n_ranges = (uint32_t)m->sm_count;
+            terr.n_tasks = (uint32_t)((total + 31) / 32);
+            terr.tasks_per_range = (terr.n_tasks + terr.n_ranges - 1) / terr.n_ranges;
+            // whole claims per range, so that only a range's last claim can be short
+            terr.tasks_per_range = (terr.tasks_per_range + TERR_CLAIM - 1) / TERR_CLAIM * TERR_CLAIM;
+            RL_CUDA(cudaMemsetAsync(scratch, 0, zero_b, s));
+            {
+                static const int sort_per_sm = [] {
+                    int v = 0;
+                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, pose_sort_kernel, CTA_THREADS, 0) != cudaSuccess) cudaGetLastError();
+                    return v < 1 ? 1 : v;
+                }();
+                int64_t grid = (int64_t)sort_per_sm * m->sm_count;   // co-resident: grid-wide barriers
+                const int64_t need = (num_poses + CTA_THREADS - 1) / CTA_THREADS;
+                if (grid > need) grid = need;
+                RL_CUDA(launch_windowed_ex(m, pose_sort_kernel, (unsigned)grid, s, false, true, m->P, d_poses, stride_floats, terr));
+            }
+#define RL_TERR2(COUNT, SMALL, PADDED)                                                                       \
+            do {                                                                                             \
+                auto kern = march_territory_kernel<FAN, COUNT, SMALL, PADDED>;                               \
+                static const int per_sm = [&] {                                                              \
+                    int v = 0;                                                                               \
+                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, CTA_THREADS, 0) != cudaSuccess) cudaGetLastError(); \
+                    return v < 1 ? 1 : v;                                                                    \
+                }();                                                                                         \
+                int64_t grid = (int64_t)per_sm * m->sm_count;                                                \
+                if (grid > blocks) grid = blocks;                                                            \
+                RL_CUDA(launch_windowed_ex(m, kern, (unsigned)grid, s, false, false, m->P, d_poses, stride_floats, d_angles, \
+                                        d_outs, total, num_beams, div, fov, inc, ctr, terr));                \
+            } while (0)
+#define RL_TERR(COUNT, SMALL) do { if (m->P.pad > 0) RL_TERR2(COUNT, SMALL, true); else RL_TERR2(COUNT, SMALL, false); } while (0)
+            if (m->count) { if (small) RL_TERR(true, true); else RL_TERR(true, false); }
+            else { if (small) RL_TERR(false, true); else RL_TERR(false, false); }
+#undef RL_TERR
+#undef RL_TERR2
+            cudaFreeAsync(scratch, s);
+            RL_CUDA(cudaGetLastError());
+            return RL_OK;
         }
+        cudaGetLastError();   // no scratch: march in the caller's order
     }
 #define RL_LAUNCH2(COUNT, SMALL, OUT, PADDED)                                                      \
     RL_CUDA(launch_windowed(m, march_pose_kernel<FAN, COUNT, SMALL, OUT, PADDED>, (unsigned)blocks, s, pdl, m->P, d_poses, \
-                            stride_floats, d_angles, d_perm, d_outs, total, num_beams, div, fov, inc, ctr, po))
+                            stride_floats, d_angles, d_outs, total, num_beams, div, fov, inc, ctr, po))
 #define RL_LAUNCH(COUNT, SMALL, OUT)                                                               \
     do { if (m->P.pad > 0) RL_LAUNCH2(COUNT, SMALL, OUT, true); else RL_LAUNCH2(COUNT, SMALL, OUT, false); } while (0)
     if (peers) {
@@ -344,7 +581,6 @@ int32_t launch_pose(rl_marcher *m, const float *d_poses, int64_t stride_rows, co
     }
 #undef RL_LAUNCH2
 #undef RL_LAUNCH
-    if (scratch) cudaFreeAsync(scratch, s);
     RL_CUDA(cudaGetLastError());
     return RL_OK;
 }
@@ -551,12 +787,26 @@ int32_t rl_marcher_create(const rl_map *map, float max_range_px, uint32_t flags,
         }
         cudaGetLastError();
     }
-    {   // poses are visited in map order when the field cannot live in L2 (RL_SORT_POSES=0/1 overrides, for measurements)
-        int l2_bytes = 0;
-        cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, map->device);
-        const size_t field = m->field_bytes ? m->field_bytes : (size_t)map->rows * map->cols * sizeof(float);
-        m->sort_poses = !(flags & RL_FLAG_NO_POSE_SORT) && m->l2_window_bytes == 0 && field > (size_t)l2_bytes;
+    {   // large batches are marched in map order by SM territories (RL_SORT_* / RL_TERRITORY override, for measurements)
+        m->sort_poses = !(flags & RL_FLAG_NO_POSE_SORT);
         if (const char *e = std::getenv("RL_SORT_POSES")) m->sort_poses = e[0] == '1' && !(flags & RL_FLAG_NO_POSE_SORT);
+        if (const char *e = std::getenv("RL_SORT_SHIFT")) { const int v = std::atoi(e); if (v >= 0 && v <= 12) m->sort_shift = v; }
+        if (const char *e = std::getenv("RL_SORT_MIN_POSES")) { const long v = std::atol(e); if (v >= 1) m->sort_min_poses = v; }
+    }
+    if (m->sort_poses) {   // stream-ordered scratch for the sort, kept by the pool between calls
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = map->device;
+        if (cudaMemPoolCreate(&m->scratch_pool, &props) == cudaSuccess) {
+            uint64_t keep = ~(uint64_t)0;
+            cudaMemPoolSetAttribute(m->scratch_pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else {
+            m->scratch_pool = nullptr;   // no pool: batches are marched in the caller's order
+            m->sort_poses = false;
+        }
+        cudaGetLastError();
     }
     cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking);
@@ -582,6 +832,7 @@ int32_t rl_marcher_destroy(rl_marcher *m)
             if (m->fork_ev[i]) cudaEventDestroy(m->fork_ev[i]);
             if (m->done_ev[i]) cudaEventDestroy(m->done_ev[i]);
         }
+        if (m->scratch_pool) { cudaDeviceSynchronize(); cudaMemPoolDestroy(m->scratch_pool); }
         cudaFreeHost(m->h_in); cudaFreeHost(m->h_out);
         cudaFree(m->d_in); cudaFree(m->d_out); cudaFree(m->d_angles); cudaFree(m->d_steps); cudaFree(m->d_field);
         for (int i = 0; i < 32; ++i) {

@@ -12,8 +12,11 @@ struct rl_marcher {
     int sm_count = 148;
     float *d_field = nullptr;    // this marcher's NaN-padded copy of the map's march field (P.pad > 0), or null
     size_t field_bytes = 0;
-    bool sort_poses = false;      // field larger than L2: large batches are marched in map order (march.cu: pose_bin_kernel)
+    // large batches are marched in map order, by SM territories (march.cu: march_territory_kernel)
+    bool sort_poses = false;
+    int sort_shift = 4;           // Morton cells of at least 16 x 16 px (larger when the map has more than 256 of them a side)
     int64_t sort_min_poses = 16384;
+    cudaMemPool_t scratch_pool = nullptr;   // the sort's stream-ordered scratch (release threshold: never)
     // host-variant staging (guarded by mu)
     std::mutex mu;
     cudaStream_t stream = nullptr, stream2 = nullptr;   // double-buffered H2D -> march -> D2H pipeline
@@ -48,15 +51,15 @@ constexpr int MARCH_CTA_THREADS = 128;   // 128-thread CTAs measured best (profi
 // preceding kernel in the stream has let its dependents go (every march kernel does so as its first
 // instruction) instead of after it has drained.
 template <typename... KArgs, typename... Args>
-cudaError_t launch_windowed(const rl_marcher *m, void (*kernel)(KArgs...), unsigned blocks, cudaStream_t s,
-                            bool pdl, Args &&...args)
+cudaError_t launch_windowed_ex(const rl_marcher *m, void (*kernel)(KArgs...), unsigned blocks, cudaStream_t s,
+                               bool pdl, bool cooperative, Args &&...args)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(blocks);
     cfg.blockDim = dim3(MARCH_CTA_THREADS);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = s;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[3];
     unsigned n = 0;
     if (m->l2_window_bytes) {
         attr[n].id = cudaLaunchAttributeAccessPolicyWindow;
@@ -72,9 +75,21 @@ cudaError_t launch_windowed(const rl_marcher *m, void (*kernel)(KArgs...), unsig
         attr[n].val.programmaticStreamSerializationAllowed = 1;
         ++n;
     }
+    if (cooperative) {   // all CTAs co-resident: the kernel uses grid-wide barriers
+        attr[n].id = cudaLaunchAttributeCooperative;
+        attr[n].val.cooperative = 1;
+        ++n;
+    }
     cfg.attrs = n ? attr : nullptr;
     cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_windowed(const rl_marcher *m, void (*kernel)(KArgs...), unsigned blocks, cudaStream_t s,
+                            bool pdl, Args &&...args)
+{
+    return launch_windowed_ex(m, kernel, blocks, s, pdl, false, std::forward<Args>(args)...);
 }
 
 // Where a device-pointer march of marcher `m` requested on `caller` actually runs.

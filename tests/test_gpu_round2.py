@@ -218,20 +218,30 @@ def test_padded_and_bounds_tested_marchers_agree(orc, big):
     assert np.array_equal(got, orc.Marcher(big["dist"], 123.75, res, big["origin"]).calc_range_fan(poses, 61, FOV))
 
 
-def test_map_order_marching_is_invisible(big):
-    """Fields larger than L2 are marched in map order (a radix sort of pose indices per call); forced here on a
-    small map: every entry point must return exactly what the caller-order march returns, at the caller's indices."""
+def _marcher_with_env(omap, mrx, env, **kw):
+    keys = ("RL_SORT_POSES", "RL_SORT_SHIFT", "RL_SORT_MIN_POSES")
+    for k in keys:
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    try:
+        return range_libc.PyRayMarchingGPU(omap, mrx, **kw)
+    finally:
+        for k in keys:
+            os.environ.pop(k, None)
+
+
+@pytest.mark.parametrize("env", [{}, {"RL_SORT_SHIFT": "0"}, {"RL_SORT_SHIFT": "7"}], ids=["cells-16px", "cells-finest", "cells-128px"])
+def test_map_order_marching_is_invisible(big, env):
+    """Large batches are marched in map order by SM territories (a counting sort of pose indices per call): every
+    entry point must return exactly what the caller-order march returns, at the caller's indices."""
     import torch
     n, R = 20000, 33
     poses = maps.sample_free_poses(big["dist"], n, 808, big["res"], big["origin"])
     poses[::997, 0] = np.nan                       # poses that convert to no cell at all
     poses[5::991, 1] = 1e30
     plain = range_libc.PyRayMarchingGPU(big["omap"], 300, flags=_native.RL_FLAG_NO_POSE_SORT)
-    os.environ["RL_SORT_POSES"] = "1"
-    try:
-        srt = range_libc.PyRayMarchingGPU(big["omap"], 300)
-    finally:
-        os.environ.pop("RL_SORT_POSES", None)
+    srt = _marcher_with_env(big["omap"], 300, dict(env, RL_SORT_POSES="1"))
+    poses[100:4000, :2] = poses[100, :2]           # thousands of poses in one cell (grouped atomics)
     dp = torch.from_numpy(poses).cuda()
     a, b = (torch.zeros(n * R, dtype=torch.float32, device="cuda") for _ in range(2))
     plain.calc_range_fan(dp, a, FOV, R)
@@ -256,6 +266,30 @@ def test_map_order_marching_is_invisible(big):
     srt.calc_range_fan(dp, b, FOV, R)
     plain.calc_range_fan(dp, a, FOV, R)
     assert srt.last_steps() == plain.last_steps() and torch.equal(a, b)
+
+
+@pytest.mark.parametrize("n,R", [(1, 1), (3, 7), (40, 1), (149, 32), (1000, 61), (4097, 270)])
+def test_territories_on_small_and_ragged_batches(big, n, R):
+    """Fewer tasks than SMs, short last claims, a last task that is not full: the territory kernel (forced on every
+    batch size here) must hand out each ray exactly once."""
+    import torch
+    poses = maps.sample_free_poses(big["dist"], n, 4242 + n, big["res"], big["origin"])
+    plain = range_libc.PyRayMarchingGPU(big["omap"], 300, flags=_native.RL_FLAG_NO_POSE_SORT)
+    srt = _marcher_with_env(big["omap"], 300, {"RL_SORT_POSES": "1", "RL_SORT_MIN_POSES": "1"})
+    dp = torch.from_numpy(poses).cuda()
+    a = torch.zeros(n * R, dtype=torch.float32, device="cuda")
+    b = torch.full((n * R + 8,), -7.0, dtype=torch.float32, device="cuda")
+    plain.calc_range_fan(dp, a, FOV, R)
+    for _ in range(3):                                                  # claims are re-zeroed per call
+        b[: n * R] = -7.0
+        srt.calc_range_fan(dp, b[: n * R], FOV, R)
+        assert torch.equal(a, b[: n * R])
+        assert bool((b[n * R:] == -7.0).all())
+    srt.count_steps(True)
+    plain.count_steps(True)
+    srt.calc_range_fan(dp, b[: n * R], FOV, R)
+    plain.calc_range_fan(dp, a, FOV, R)
+    assert srt.last_steps() == plain.last_steps()
 
 
 # --------------------------------------------------------------------------- fused all-gather, repeat_angles + 16-byte stores

@@ -3,7 +3,8 @@
   steady   K back-to-back config-2 launches under one event pair: stream order vs two-stream vs PDL
   calib    4-byte gather and full-sector L2 calibrations
   cfg      configs 3 and 5 (one GPU's share), device time
-    python tools/r02_probe.py [edt] [steady] [calib] [cfg]
+  terr     map order + SM territories on configs 3 / 5, per variant
+    python tools/r02_probe.py [edt] [steady] [calib] [cfg] [terr]
 Prints one JSON line per measurement."""
 import json
 import os
@@ -186,6 +187,83 @@ def cfg():
         ms = timeit(lambda: [rm5.calc_range_fan(poses5[a:a + chunk], out5[:chunk * b5], FOV, b5) for a in range(0, n5, chunk)])
         print(json.dumps({"probe": "cfg5_share_in_pieces_of_262144", "map_order": sort == "1", "ms": ms,
                           "grays_per_s": n5 * b5 / ms / 1e6}), flush=True)
+
+
+VARIANTS = [
+    ("caller order", {"RL_SORT_POSES": "0"}),
+    ("territories, 16 px cells (default)", {"RL_SORT_POSES": "1"}),
+    ("territories, 4 px cells", {"RL_SORT_POSES": "1", "RL_SORT_SHIFT": "2"}),
+    ("territories, 64 px cells", {"RL_SORT_POSES": "1", "RL_SORT_SHIFT": "6"}),
+]
+
+
+def with_env(env, make):
+    keys = ("RL_SORT_POSES", "RL_SORT_SHIFT", "RL_SORT_MIN_POSES")
+    for k in keys:
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    try:
+        return make()
+    finally:
+        for k in keys:
+            os.environ.pop(k, None)
+
+
+def terr():
+    """Map order + SM territories: configs 3 and 5 (one GPU's share) and a clustered particle set, per variant."""
+    omap, y, dist = config2()
+    n, a = 1_000_000, 60
+    uniform = maps.sample_free_poses(dist, n, 303, y.resolution, y.origin)
+    # a particle filter's cloud: all poses within ~1 m of one place, headings within +-0.3 rad
+    rng = np.random.default_rng(9)
+    c = uniform[12345]
+    cloud = np.empty((n, 3), np.float32)
+    cloud[:, 0] = c[0] + rng.normal(0, 0.5, n)
+    cloud[:, 1] = c[1] + rng.normal(0, 0.5, n)
+    cloud[:, 2] = c[2] + rng.normal(0, 0.3, n)
+    angles = torch.from_numpy(np.linspace(-FOV / 2, FOV / 2, a, endpoint=False).astype(np.float32)).cuda()
+    out = torch.empty(n * a, dtype=torch.float32, device="cuda")
+    ref = {}
+    for name, env in VARIANTS:
+        rm = with_env(env, lambda: range_libc.PyRayMarchingGPU(omap, 300))
+        for label, ps in (("cfg3 uniform", uniform), ("cfg3-shaped particle cloud", cloud)):
+            poses = torch.from_numpy(ps).cuda()
+            ms = timeit(lambda: rm.calc_range_repeat_angles(poses, angles, out))
+            chk = float(out.double().sum().item())
+            ref.setdefault(label, out.clone())
+            print(json.dumps({"probe": "terr", "case": label, "variant": name, "ms": ms, "grays_per_s": n * a / ms / 1e6,
+                              "identical": bool(torch.equal(out, ref[label])), "checksum": chk}), flush=True)
+        del rm
+    # config 2 must not care (4096 poses < the sort threshold) -- and what if it did sort?
+    p2 = torch.from_numpy(maps.sample_free_poses(dist, 4096, 1000, y.resolution, y.origin)).cuda()
+    out2 = torch.empty(4096 * 1080, dtype=torch.float32, device="cuda")
+    for name, env in (("caller order", {"RL_SORT_POSES": "0"}), ("default", {}),
+                      ("forced territories", {"RL_SORT_POSES": "1", "RL_SORT_MIN_POSES": "1"})):
+        rm = with_env(env, lambda: range_libc.PyRayMarchingGPU(omap, 300))
+        ms = timeit(lambda: rm.calc_range_fan(p2, out2, FOV, 1080), reps=20)
+        print(json.dumps({"probe": "terr", "case": "cfg2 warm", "variant": name, "ms": ms, "grays_per_s": 4096 * 1080 / ms / 1e6}), flush=True)
+        del rm
+    del omap, out, out2
+    img = maps.synth_map(8192, 5678)
+    y5 = maps.synth_yaml(8192)
+    path = f"/tmp/_rl_probe5_{os.getpid()}.pgm"
+    maps.write_pgm(path, img)
+    y5.image = path
+    omap5 = range_libc.PyOMap(y5)
+    os.unlink(path)
+    dist5 = omap5.dist()
+    n5, b5 = 2_000_000, 270
+    poses5 = torch.from_numpy(maps.sample_free_poses(dist5, n5, 505, y5.resolution, y5.origin)).cuda()
+    out5 = torch.empty(n5 * b5, dtype=torch.float32, device="cuda")
+    ref5 = None
+    for name, env in VARIANTS:
+        rm5 = with_env(env, lambda: range_libc.PyRayMarchingGPU(omap5, 300))
+        ms = timeit(lambda: rm5.calc_range_fan(poses5, out5, FOV, b5), reps=3)
+        if ref5 is None:
+            ref5 = out5.clone()
+        print(json.dumps({"probe": "terr", "case": "cfg5 share (2M poses x 270)", "variant": name, "ms": ms,
+                          "grays_per_s": n5 * b5 / ms / 1e6, "identical": bool(torch.equal(out5, ref5))}), flush=True)
+        del rm5
 
 
 if __name__ == "__main__":
