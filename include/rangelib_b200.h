@@ -79,10 +79,12 @@ typedef enum rl_status {
 /* p = ceil(max_range_px) + 16 and removes the per-step bounds test); the bounds-tested kernels are used,      */
 /* as they are automatically for max_range_px > 2048.  Results are identical either way.                     */
 #define RL_FLAG_NO_PADDED_FIELD 2u
-/* When the field is larger than the L2 cache (an 8192^2 map: 256 MiB), batches of >= 16384 poses are MARCHED  */
-/* in map order (64 x 64 px bins; one radix sort of pose indices per call, scratch from the stream's memory   */
-/* pool) so that the poses in flight share their neighbourhoods in L2; inputs are read and ranges written at  */
-/* the caller's indices, results are identical.  This flag keeps the caller's order.                          */
+/* Large batches of poses are MARCHED in map order by SM territories: one counting sort of the pose indices by  */
+/* Morton cell per call (scratch from a pool the marcher owns), then every SM works through one contiguous range */
+/* of that order, so neighbouring poses share their field cells in its L1.  Applied when the poses are dense     */
+/* (>= one per 16 map cells and >= 32 M rays) or the field is larger than L2 (>= 16 384 poses and >= 16 M rays). */
+/* Poses are read and ranges written at the caller's indices; results are identical.  This flag keeps the       */
+/* caller's order.                                                                                               */
 #define RL_FLAG_NO_POSE_SORT 4u
 
 /* dist2 value of a cell from which no occupied cell is reachable (empty map) */

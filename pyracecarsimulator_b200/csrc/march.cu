@@ -191,8 +191,8 @@ pad_field_kernel(const float *__restrict__ src, int rows, int cols, int pad, flo
 //   2. march_territory_kernel cuts that order into one contiguous range per SM.  The warps resident on an SM claim 32-ray tasks from
 //      their SM's own range (one atomic per TERR_CLAIM tasks), so at any moment an SM works on a few dozen
 //      neighbouring poses and sweeps slowly through one compact territory of the map, whose field cells stay in its
-//      L1 (74 % hits on config 3, L2 sector reads down 3.2 x).  A warp whose range is used up helps out in the range
-//      with the most work left.
+//      L1 (74 % hits on config 3, L2 sector reads down 3.2 x).  A warp whose range is used up helps out in the next
+//      range that has work left.
 // The kernel still reads pose k and writes its ranges at k * num_beams: only the ORDER of the work changes, not a
 // bit of any result (tests/test_gpu_round2.py::test_map_order_marching_is_invisible).
 namespace cg = cooperative_groups;
@@ -233,22 +233,21 @@ __device__ __forceinline__ uint32_t territory_len(const Territories &T, uint32_t
     return base < T.n_tasks ? (uint32_t)min((uint64_t)T.tasks_per_range, (uint64_t)T.n_tasks - base) : 0u;
 }
 
-// The range with the most unclaimed tasks (all lanes get the same answer), or 0xffffffff when none is left.
-__device__ __forceinline__ uint32_t busiest_territory(const Territories &T, unsigned lane)
+// The next range after `home` (in circular order) that still has unclaimed tasks, or 0xffffffff when none is
+// left (all lanes get the same answer).  Thieves from different SMs start from different homes, so they spread
+// over different victims instead of all draining the same one.
+__device__ __forceinline__ uint32_t next_territory(const Territories &T, uint32_t home, unsigned lane)
 {
-    uint32_t best_left = 0, best_r = 0xffffffffu;
-    for (uint32_t q = lane; q < T.n_ranges; q += 32) {
-        const uint32_t c = *reinterpret_cast<const volatile uint32_t *>(T.claims + q * TERR_CLAIM_STRIDE);
-        const uint32_t len = territory_len(T, q);
-        const uint32_t left = c < len ? len - c : 0u;
-        if (left > best_left) { best_left = left; best_r = q; }
+    for (uint32_t base = 1; base < T.n_ranges; base += 32) {
+        const uint32_t off = base + lane;
+        uint32_t q = home + off;
+        if (q >= T.n_ranges) q -= T.n_ranges;
+        bool has = false;
+        if (off < T.n_ranges) has = *reinterpret_cast<const volatile uint32_t *>(T.claims + q * TERR_CLAIM_STRIDE) < territory_len(T, q);
+        const unsigned found = __ballot_sync(0xffffffffu, has);
+        if (found) return __shfl_sync(0xffffffffu, q, __ffs(found) - 1);
     }
-#pragma unroll
-    for (int off = 16; off; off >>= 1) {
-        const uint32_t ol = __shfl_xor_sync(0xffffffffu, best_left, off), orr = __shfl_xor_sync(0xffffffffu, best_r, off);
-        if (ol > best_left || (ol == best_left && orr < best_r)) { best_left = ol; best_r = orr; }
-    }
-    return best_left ? best_r : 0xffffffffu;
+    return 0xffffffffu;
 }
 
 // One atomic per distinct key of the warp: a particle cloud puts a million poses into a few dozen cells, and
@@ -275,12 +274,16 @@ __device__ __forceinline__ uint32_t grouped_atomic_add(uint32_t *counters, uint3
     return pos;
 }
 
-__global__ void __launch_bounds__(CTA_THREADS)
+// Few, large CTAs: a grid-wide barrier costs one same-address atomic per CTA (2 368 CTAs of 128 threads spent
+// more time in the three barriers than in the sort).
+constexpr int SORT_THREADS = 1024;
+
+__global__ void __launch_bounds__(SORT_THREADS)
 pose_sort_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_stride_floats, Territories T)
 {
     cg::grid_group grid = cg::this_grid();
-    __shared__ uint32_t warp_sum[CTA_THREADS / 32];
-    const int64_t tid = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x, nthreads = (int64_t)gridDim.x * CTA_THREADS;
+    __shared__ uint32_t warp_sum[SORT_THREADS / 32];
+    const int64_t tid = (int64_t)blockIdx.x * SORT_THREADS + threadIdx.x, nthreads = (int64_t)gridDim.x * SORT_THREADS;
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // 1. keys + histogram (whole warps iterate together: the grouped atomic is warp-synchronous)
     for (int64_t k0 = tid - lane; k0 < T.num_poses; k0 += nthreads) {
@@ -298,26 +301,24 @@ pose_sort_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_st
         grouped_atomic_add<false>(T.cursor, key, valid);
     }
     grid.sync();
-    // 2a. every CTA scans one tile of SORT_TILE bins: count -> exclusive offset inside the tile; tile total -> tile_off
+    // 2a. every warp scans tiles of SORT_TILE bins: count -> exclusive offset inside the tile; tile total -> tile_off
     const uint32_t n_tiles = T.n_bins / SORT_TILE;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        if (warp == 0) {
-            const uint32_t c = T.cursor[tile * SORT_TILE + lane];
-            uint32_t inc = c;
+    for (uint32_t tile = (uint32_t)(tid >> 5); tile < n_tiles; tile += (uint32_t)(nthreads >> 5)) {
+        const uint32_t c = T.cursor[tile * SORT_TILE + lane];
+        uint32_t inc = c;
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, off);
-                if ((int)lane >= off) inc += o;
-            }
-            T.cursor[tile * SORT_TILE + lane] = inc - c;
-            if (lane == 31) T.tile_off[tile] = inc;
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, inc, off);
+            if ((int)lane >= off) inc += o;
         }
+        T.cursor[tile * SORT_TILE + lane] = inc - c;
+        if (lane == 31) T.tile_off[tile] = inc;
     }
     grid.sync();
     // 2b. CTA 0 turns the tile totals into exclusive offsets
     if (blockIdx.x == 0) {
         uint32_t carry = 0;
-        for (uint32_t base = 0; base < n_tiles; base += CTA_THREADS) {
+        for (uint32_t base = 0; base < n_tiles; base += SORT_THREADS) {
             const uint32_t i = base + threadIdx.x;
             const uint32_t c = i < n_tiles ? T.tile_off[i] : 0u;
             uint32_t inc = c;
@@ -331,7 +332,7 @@ pose_sort_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_st
             uint32_t before = carry;
             for (unsigned w = 0; w < warp; ++w) before += warp_sum[w];
             if (i < n_tiles) T.tile_off[i] = before + inc - c;
-            for (unsigned w = 0; w < CTA_THREADS / 32; ++w) carry += warp_sum[w];
+            for (unsigned w = 0; w < SORT_THREADS / 32; ++w) carry += warp_sum[w];
             __syncthreads();
         }
     }
@@ -363,8 +364,8 @@ march_territory_kernel(MarchParams P, const float *__restrict__ poses, int64_t p
         uint32_t c = 0;
         if (lane == 0) c = atomicAdd(T.claims + r * TERR_CLAIM_STRIDE, (uint32_t)TERR_CLAIM);
         c = __shfl_sync(0xffffffffu, c, 0);
-        if (c >= len) {   // this range is used up: help where the most work is left
-            r = busiest_territory(T, lane);
+        if (c >= len) {   // this range is used up: help in the next one that has work left
+            r = next_territory(T, r, lane);
             continue;
         }
         const uint32_t first = r * T.tasks_per_range + c, last = first + min((uint32_t)TERR_CLAIM, len - c);
@@ -498,8 +499,16 @@ int32_t launch_pose(rl_marcher *m, const float *d_poses, int64_t stride_rows, co
     const int64_t stride_floats = stride_rows * 3;
     const PeerOut po = peers ? *peers : PeerOut{};
     // large batches are marched in map order, by SM territories (see march_territory_kernel); scratch is stream-ordered
-    if (m->sort_poses && !peers && num_poses >= m->sort_min_poses && num_poses < ((int64_t)1 << 32) &&
-        blocks * (CTA_THREADS / 32) < ((int64_t)1 << 32)) {
+    // Worth it when the poses are dense enough to share field cells (L2-resident field: at least one pose per 16 map
+    // cells and 32 M rays -- 1 M x 60 on a 2049^2 map gains 19 %, 65 536 x 1080 gains 3 %, smaller batches lose to
+    // the sort's ~50 us) or when the field is larger than L2 and locality saves DRAM sector gathers (config 5: +80 %).
+    bool by_territories = false;
+    if (m->sort_poses && !peers && num_poses < ((int64_t)1 << 32) && blocks * (CTA_THREADS / 32) < ((int64_t)1 << 32)) {
+        if (m->sort_forced) by_territories = num_poses >= m->sort_min_poses;
+        else if (m->field_beyond_l2) by_territories = num_poses >= 16384 && total >= ((int64_t)16 << 20);
+        else by_territories = num_poses * 16 >= (int64_t)m->P.rows * m->P.cols && total >= ((int64_t)32 << 20);
+    }
+    if (by_territories) {
         Territories terr{};
         int side = m->P.rows > m->P.cols ? m->P.rows : m->P.cols, side_bits = 1;
         terr.shift = m->sort_shift;
@@ -531,13 +540,22 @@ int32_t launch_pose(rl_marcher *m, const float *d_poses, int64_t stride_rows, co
             {
                 static const int sort_per_sm = [] {
                     int v = 0;
-                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, pose_sort_kernel, CTA_THREADS, 0) != cudaSuccess) cudaGetLastError();
+                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, pose_sort_kernel, SORT_THREADS, 0) != cudaSuccess) cudaGetLastError();
                     return v < 1 ? 1 : v;
                 }();
                 int64_t grid = (int64_t)sort_per_sm * m->sm_count;   // co-resident: grid-wide barriers
-                const int64_t need = (num_poses + CTA_THREADS - 1) / CTA_THREADS;
+                const int64_t need = (num_poses + SORT_THREADS - 1) / SORT_THREADS;
                 if (grid > need) grid = need;
-                RL_CUDA(launch_windowed_ex(m, pose_sort_kernel, (unsigned)grid, s, false, true, m->P, d_poses, stride_floats, terr));
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)grid);
+                cfg.blockDim = dim3(SORT_THREADS);
+                cfg.stream = s;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeCooperative;
+                attr[0].val.cooperative = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                RL_CUDA(cudaLaunchKernelEx(&cfg, pose_sort_kernel, m->P, d_poses, stride_floats, terr));
             }
 #define RL_TERR2(COUNT, SMALL, PADDED)                                                                       \
             do {                                                                                             \
@@ -789,7 +807,13 @@ int32_t rl_marcher_create(const rl_map *map, float max_range_px, uint32_t flags,
     }
     {   // large batches are marched in map order by SM territories (RL_SORT_* / RL_TERRITORY override, for measurements)
         m->sort_poses = !(flags & RL_FLAG_NO_POSE_SORT);
-        if (const char *e = std::getenv("RL_SORT_POSES")) m->sort_poses = e[0] == '1' && !(flags & RL_FLAG_NO_POSE_SORT);
+        if (const char *e = std::getenv("RL_SORT_POSES")) {   // 1: every batch of at least RL_SORT_MIN_POSES poses, 0: none
+            m->sort_poses = e[0] == '1' && !(flags & RL_FLAG_NO_POSE_SORT);
+            m->sort_forced = m->sort_poses;
+        }
+        int l2_bytes = 0;
+        cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, map->device);
+        m->field_beyond_l2 = (m->field_bytes ? m->field_bytes : (size_t)map->rows * map->cols * sizeof(float)) > (size_t)l2_bytes;
         if (const char *e = std::getenv("RL_SORT_SHIFT")) { const int v = std::atoi(e); if (v >= 0 && v <= 12) m->sort_shift = v; }
         if (const char *e = std::getenv("RL_SORT_MIN_POSES")) { const long v = std::atol(e); if (v >= 1) m->sort_min_poses = v; }
     }

@@ -14,8 +14,10 @@ struct rl_marcher {
     size_t field_bytes = 0;
     // large batches are marched in map order, by SM territories (march.cu: march_territory_kernel)
     bool sort_poses = false;
+    bool sort_forced = false;     // RL_SORT_POSES=1: every batch of at least sort_min_poses poses (tests, measurements)
+    bool field_beyond_l2 = false;
     int sort_shift = 4;           // Morton cells of at least 16 x 16 px (larger when the map has more than 256 of them a side)
-    int64_t sort_min_poses = 16384;
+    int64_t sort_min_poses = 1;
     cudaMemPool_t scratch_pool = nullptr;   // the sort's stream-ordered scratch (release threshold: never)
     // host-variant staging (guarded by mu)
     std::mutex mu;

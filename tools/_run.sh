@@ -1,10 +1,12 @@
 mkdir -p gpurun_out
-(timeout 900 python -m pytest tests/test_gpu_round2.py tests/test_gpu_march.py -x -q 2>&1 | tail -6) > gpurun_out/r2o_tests.log 2>&1
-timeout 900 python tools/r02_probe.py terr > gpurun_out/r2o_terr.jsonl 2> gpurun_out/r2o_terr.err
-tail -6 gpurun_out/r2o_tests.log
-cat gpurun_out/r2o_terr.jsonl
-tail -3 gpurun_out/r2o_terr.err
-M=gpu__time_duration.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_hit.sum,lts__t_sectors_srcunit_tex_op_read.sum,smsp__inst_executed.sum,launch__grid_size,launch__registers_per_thread
-cd tools
-timeout 900 ncu -k regex:"march|sort" --metrics $M --clock-control none --csv --log-file ../gpurun_out/r2o_terr_ncu.csv python r02_terr_ncu.py > ../gpurun_out/r2o_terr_ncu.log 2>&1
-tail -3 ../gpurun_out/r2o_terr_ncu.log
+(timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -6) > gpurun_out/r2r_tests.log 2>&1
+tail -6 gpurun_out/r2r_tests.log
+timeout 900 python bench.py > gpurun_out/r2r_bench_n1.json 2> gpurun_out/r2r_bench_n1.err
+tail -c 600 gpurun_out/r2r_bench_n1.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2r_bench_n1.json').read().strip().splitlines()[-1])
+print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'])
+for k in ('config3','config5','config4','config1'):
+    c=d['configs'][k]; print(k,{x:c[x] for x in c if x in('kernel_ms','rays_per_s','us_per_scan')})
+PY

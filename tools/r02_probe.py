@@ -243,6 +243,23 @@ def terr():
         ms = timeit(lambda: rm.calc_range_fan(p2, out2, FOV, 1080), reps=20)
         print(json.dumps({"probe": "terr", "case": "cfg2 warm", "variant": name, "ms": ms, "grays_per_s": 4096 * 1080 / ms / 1e6}), flush=True)
         del rm
+    # where should the threshold be?  N poses x 1080 beams and N poses x 60 angles, caller order vs territories
+    for nb, kind in ((1080, "fan"), (60, "angles")):
+        for npz in (2048, 4096, 8192, 16384, 65536):
+            if npz * nb > 80_000_000:
+                continue
+            pz = torch.from_numpy(maps.sample_free_poses(dist, npz, 77 + npz, y.resolution, y.origin)).cuda()
+            oz = torch.empty(npz * nb, dtype=torch.float32, device="cuda")
+            row = {"probe": "terr_threshold", "poses": npz, "beams": nb}
+            for name, env in (("caller_order", {"RL_SORT_POSES": "0"}), ("territories", {"RL_SORT_POSES": "1", "RL_SORT_MIN_POSES": "1"})):
+                rm = with_env(env, lambda: range_libc.PyRayMarchingGPU(omap, 300))
+                if kind == "fan":
+                    row[name + "_ms"] = timeit(lambda: rm.calc_range_fan(pz, oz, FOV, nb), reps=9)
+                else:
+                    row[name + "_ms"] = timeit(lambda: rm.calc_range_repeat_angles(pz, angles, oz), reps=9)
+                del rm
+            print(json.dumps(row), flush=True)
+            del pz, oz
     del omap, out, out2
     img = maps.synth_map(8192, 5678)
     y5 = maps.synth_yaml(8192)
