@@ -191,8 +191,8 @@ pad_field_kernel(const float *__restrict__ src, int rows, int cols, int pad, flo
 //   2. march_territory_kernel cuts that order into one contiguous range per SM.  The warps resident on an SM claim 32-ray tasks from
 //      their SM's own range (one atomic per TERR_CLAIM tasks), so at any moment an SM works on a few dozen
 //      neighbouring poses and sweeps slowly through one compact territory of the map, whose field cells stay in its
-//      L1 (74 % hits on config 3, L2 sector reads down 3.2 x).  A warp whose range is used up helps out in the next
-//      range that has work left.
+//      L1 (74 % hits on config 3, L2 sector reads down 3.2 x).  A warp whose range is used up helps out in the range
+//      with the most work left.
 // The kernel still reads pose k and writes its ranges at k * num_beams: only the ORDER of the work changes, not a
 // bit of any result (tests/test_gpu_round2.py::test_map_order_marching_is_invisible).
 namespace cg = cooperative_groups;
@@ -233,59 +233,122 @@ __device__ __forceinline__ uint32_t territory_len(const Territories &T, uint32_t
     return base < T.n_tasks ? (uint32_t)min((uint64_t)T.tasks_per_range, (uint64_t)T.n_tasks - base) : 0u;
 }
 
-// The next range after `home` (in circular order) that still has unclaimed tasks, or 0xffffffff when none is
-// left (all lanes get the same answer).  Thieves from different SMs start from different homes, so they spread
-// over different victims instead of all draining the same one.
-__device__ __forceinline__ uint32_t next_territory(const Territories &T, uint32_t home, unsigned lane)
+// The range with the most unclaimed tasks (all lanes get the same answer), or 0xffffffff when none is left.
+// (Helping in the NEXT range with work left instead -- so that thieves spread out -- measured 5 % slower on uniform
+// poses and 24 % slower on a particle cloud, whose ranges differ a lot in cost: the fullest range is the one that
+// would finish last.)
+__device__ __forceinline__ uint32_t busiest_territory(const Territories &T, unsigned lane)
 {
-    for (uint32_t base = 1; base < T.n_ranges; base += 32) {
-        const uint32_t off = base + lane;
-        uint32_t q = home + off;
-        if (q >= T.n_ranges) q -= T.n_ranges;
-        bool has = false;
-        if (off < T.n_ranges) has = *reinterpret_cast<const volatile uint32_t *>(T.claims + q * TERR_CLAIM_STRIDE) < territory_len(T, q);
-        const unsigned found = __ballot_sync(0xffffffffu, has);
-        if (found) return __shfl_sync(0xffffffffu, q, __ffs(found) - 1);
+    uint32_t best_left = 0, best_r = 0xffffffffu;
+    for (uint32_t q = lane; q < T.n_ranges; q += 32) {
+        const uint32_t c = *reinterpret_cast<const volatile uint32_t *>(T.claims + q * TERR_CLAIM_STRIDE);
+        const uint32_t len = territory_len(T, q);
+        const uint32_t left = c < len ? len - c : 0u;
+        if (left > best_left) { best_left = left; best_r = q; }
     }
-    return 0xffffffffu;
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        const uint32_t ol = __shfl_xor_sync(0xffffffffu, best_left, off), orr = __shfl_xor_sync(0xffffffffu, best_r, off);
+        if (ol > best_left || (ol == best_left && orr < best_r)) { best_left = ol; best_r = orr; }
+    }
+    return best_left ? best_r : 0xffffffffu;
 }
 
-// One atomic per distinct key of the warp: a particle cloud puts a million poses into a few dozen cells, and
-// same-address atomics are served one after the other.  Returns this lane's rank among the warp's lanes with
-// its key plus the value the leader's atomic returned (valid for every lane of the group).
-template <bool WANT_POS>
-__device__ __forceinline__ uint32_t grouped_atomic_add(uint32_t *counters, uint32_t key, bool valid)
+// Counting with two levels of aggregation.  A particle cloud puts a million poses into a few dozen cells, and
+// atomics on one address are served one after the other (a 1 M-pose cloud spent 100 us in this sort with one global
+// atomic per warp and key).  So (1) the lanes of a warp that hold the same key act through one leader
+// (__match_any_sync), and (2) every CTA counts its own poses in a small shared-memory hash table first and talks to
+// the global counters once per distinct key: one atomic per (CTA, key) to add its count, one to reserve its slots
+// in the scatter phase.  Keys that find no room in the table (four probes) go to the global counters directly.
+constexpr int SORT_THREADS = 1024;   // few, large CTAs: a grid-wide barrier costs one same-address atomic per CTA
+constexpr int SORT_SLOT_BITS = 9;    // 512 slots, 6 KB: what is taken from the SM's L1 carve-out stays small
+constexpr int SORT_SLOTS = 1 << SORT_SLOT_BITS;
+constexpr int SORT_FILL = SORT_SLOTS / 2;   // no new keys beyond this: spread-out poses gain nothing from the table
+constexpr int SORT_PROBES = 3;
+constexpr uint32_t SLOT_EMPTY = 0xffffffffu;
+
+struct SortTable {
+    uint32_t key[SORT_SLOTS];
+    uint32_t cnt[SORT_SLOTS];    // phase 1: poses of this CTA with the key; phase 3: handed out so far
+    uint32_t base[SORT_SLOTS];   // phase 3: first slot of the block this CTA reserved for the key ...
+    uint32_t room[SORT_SLOTS];   // ... and its length (the table's count of phase 1)
+    uint32_t used;
+};
+
+// A key sits in the first slot of its probe sequence that was empty when it arrived and slots never empty again, so
+// a lookup that meets an empty slot knows the key is not in the table.  No new key is admitted once the table is
+// half full -- a racy test: a key may be refused for one warp (counted globally) and admitted for a later one, which
+// is why the scatter phase fills a key's reserved block by arrival and sends the overflow to the global counter
+// (sort_account): per (CTA, key) the table and the global counter hand out exactly as many slots as each counted.
+template <bool INSERT>
+__device__ __forceinline__ int table_slot(SortTable &tb, uint32_t key)
+{
+    uint32_t s = (key * 2654435761u) >> (32 - SORT_SLOT_BITS);
+#pragma unroll
+    for (int p = 0; p < SORT_PROBES; ++p, s = (s + 1) & (SORT_SLOTS - 1)) {
+        uint32_t cur = *reinterpret_cast<volatile uint32_t *>(&tb.key[s]);
+        if (cur == key) return (int)s;
+        if (cur == SLOT_EMPTY) {
+            if (!INSERT || *reinterpret_cast<volatile uint32_t *>(&tb.used) >= (uint32_t)SORT_FILL) return -1;
+            cur = atomicCAS(&tb.key[s], SLOT_EMPTY, key);
+            if (cur == SLOT_EMPTY) { atomicAdd(&tb.used, 1u); return (int)s; }
+            if (cur == key) return (int)s;
+        }
+    }
+    return -1;
+}
+
+// Phase 1 (SCATTER = false): count this warp's keys.  Phase 3 (SCATTER = true): returns this lane's position
+// inside its key's bin.  Warp-synchronous; lanes with !valid only take part in the votes.
+template <bool SCATTER>
+__device__ __forceinline__ uint32_t sort_account(SortTable &tb, uint32_t *cursor, uint32_t key, bool valid)
 {
     const unsigned active = __ballot_sync(0xffffffffu, valid);
     uint32_t pos = 0;
     if (valid) {
+        const unsigned lane = threadIdx.x & 31;
         const unsigned peers = __match_any_sync(active, key);
         const int leader = __ffs(peers) - 1;
-        const unsigned lane = threadIdx.x & 31;
-        if (WANT_POS) {
-            uint32_t base = 0;
-            if ((int)lane == leader) base = atomicAdd(counters + key, (uint32_t)__popc(peers));
-            base = __shfl_sync(peers, base, leader);
-            pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-        } else if ((int)lane == leader) {
-            atomicAdd(counters + key, (uint32_t)__popc(peers));   // result unused: a fire-and-forget reduction
+        const uint32_t n = (uint32_t)__popc(peers);
+        uint32_t block_first = 0, block_n = 0, global_first = 0;   // this group's share of the CTA's block, the rest
+        if ((int)lane == leader) {
+            const int slot = SCATTER ? table_slot<false>(tb, key) : table_slot<true>(tb, key);
+            if (slot >= 0) {
+                const uint32_t local = atomicAdd(&tb.cnt[slot], n);
+                if (SCATTER) {
+                    const uint32_t room = tb.room[slot];
+                    block_n = room > local ? min(n, room - local) : 0u;
+                    block_first = tb.base[slot] + local;
+                }
+            }
+            if (slot < 0 || (SCATTER && block_n < n)) {
+                const uint32_t g = atomicAdd(cursor + key, n - block_n);
+                if (SCATTER) global_first = g;
+            }
+        }
+        if (SCATTER) {
+            block_first = __shfl_sync(peers, block_first, leader);
+            block_n = __shfl_sync(peers, block_n, leader);
+            global_first = __shfl_sync(peers, global_first, leader);
+            const uint32_t rank = (uint32_t)__popc(peers & ((1u << lane) - 1u));
+            pos = rank < block_n ? block_first + rank : global_first + (rank - block_n);
         }
     }
     return pos;
 }
 
-// Few, large CTAs: a grid-wide barrier costs one same-address atomic per CTA (2 368 CTAs of 128 threads spent
-// more time in the three barriers than in the sort).
-constexpr int SORT_THREADS = 1024;
-
 __global__ void __launch_bounds__(SORT_THREADS)
 pose_sort_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_stride_floats, Territories T)
 {
     cg::grid_group grid = cg::this_grid();
+    __shared__ SortTable tb;
     __shared__ uint32_t warp_sum[SORT_THREADS / 32];
     const int64_t tid = (int64_t)blockIdx.x * SORT_THREADS + threadIdx.x, nthreads = (int64_t)gridDim.x * SORT_THREADS;
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // 1. keys + histogram (whole warps iterate together: the grouped atomic is warp-synchronous)
+    for (int s = threadIdx.x; s < SORT_SLOTS; s += SORT_THREADS) { tb.key[s] = SLOT_EMPTY; tb.cnt[s] = 0; }
+    if (threadIdx.x == 0) tb.used = 0;
+    __syncthreads();
+    // 1. keys + histogram (whole warps iterate together: the accounting is warp-synchronous)
     for (int64_t k0 = tid - lane; k0 < T.num_poses; k0 += nthreads) {
         const int64_t k = k0 + lane;
         const bool valid = k < T.num_poses;
@@ -298,8 +361,11 @@ pose_sort_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_st
             key = (spread_bits8((uint32_t)(row >> T.shift)) << 1) | spread_bits8((uint32_t)(col >> T.shift));
             T.keys[k] = (uint16_t)key;
         }
-        grouped_atomic_add<false>(T.cursor, key, valid);
+        sort_account<false>(tb, T.cursor, key, valid);
     }
+    __syncthreads();
+    for (int s = threadIdx.x; s < SORT_SLOTS; s += SORT_THREADS)
+        if (tb.key[s] != SLOT_EMPTY) atomicAdd(T.cursor + tb.key[s], tb.cnt[s]);
     grid.sync();
     // 2a. every warp scans tiles of SORT_TILE bins: count -> exclusive offset inside the tile; tile total -> tile_off
     const uint32_t n_tiles = T.n_bins / SORT_TILE;
@@ -336,13 +402,20 @@ pose_sort_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_st
             __syncthreads();
         }
     }
-    grid.sync();
-    // 3. scatter the pose indices to their cells' slots
+    // 3. scatter the pose indices to their cells' slots; the CTA first reserves a block per key of its table
+    for (int s = threadIdx.x; s < SORT_SLOTS; s += SORT_THREADS) {
+        if (tb.key[s] != SLOT_EMPTY) {
+            tb.room[s] = tb.cnt[s];
+            tb.base[s] = atomicAdd(T.cursor + tb.key[s], tb.cnt[s]);
+            tb.cnt[s] = 0;
+        }
+    }
+    grid.sync();   // (also the CTA barrier between the reservation and its use)
     for (int64_t k0 = tid - lane; k0 < T.num_poses; k0 += nthreads) {
         const int64_t k = k0 + lane;
         const bool valid = k < T.num_poses;
         const uint32_t key = valid ? T.keys[k] : 0u;
-        const uint32_t pos = grouped_atomic_add<true>(T.cursor, key, valid);
+        const uint32_t pos = sort_account<true>(tb, T.cursor, key, valid);
         if (valid) T.perm[T.tile_off[key / SORT_TILE] + pos] = (uint32_t)k;
     }
 }
@@ -364,8 +437,8 @@ march_territory_kernel(MarchParams P, const float *__restrict__ poses, int64_t p
         uint32_t c = 0;
         if (lane == 0) c = atomicAdd(T.claims + r * TERR_CLAIM_STRIDE, (uint32_t)TERR_CLAIM);
         c = __shfl_sync(0xffffffffu, c, 0);
-        if (c >= len) {   // this range is used up: help in the next one that has work left
-            r = next_territory(T, r, lane);
+        if (c >= len) {   // this range is used up: help where the most work is left
+            r = busiest_territory(T, lane);
             continue;
         }
         const uint32_t first = r * T.tasks_per_range + c, last = first + min((uint32_t)TERR_CLAIM, len - c);
