@@ -558,7 +558,11 @@ def run_native(args, rank, world, local_rank):
                             "L2-resident dependent gather: DRAM traffic is the cold distance field only; `l2` and "
                             "`issue` are the views that bound it",
                     "l2": None if not lts_sectors else {
-                        "bound": "L2 sector bandwidth (random full-sector reads, measured live)",
+                        "bound": "L2 gather rate as the SMs see it: random full-sector reads, measured live.  It equals ONE 32-byte sector "
+                                 "per clock per SM (SMs x SM clock, `one_sector_per_clk_per_sm`): the rate at which an SM's L1 can "
+                                 "send misses to L2 (ncu l1tex__m_l1tex2xbar_req_cycles_active), not an L2-slice limit -- so L1 hits "
+                                 "are what relieves it (profiles/r02_territories_ncu.csv)",
+                        "one_sector_per_clk_per_sm_gsectors_per_s": sms * (clocks["sm_mhz"] or 0) * 1e-3,
                         "achieved": lts_sectors * 32.0 / (kernel_ms * 1e-3) / 1e9, "peak": sector_gps * 32.0, "unit": "GB/s",
                         "frac": lts_sectors / (kernel_ms * 1e-3) / (sector_gps * 1e9),
                         "lts_sectors_per_launch": lts_sectors, "lts_bytes_per_launch": lts_bytes,
@@ -787,7 +791,9 @@ def config3(c):
            "rays": rays, "kernel_ms": ms, "rays_per_s": rays / (ms * 1e-3), "march_steps_per_ray": steps / rays,
            "algorithmic_bytes": alg, "achieved_gbs": alg / c.world / (ms * 1e-3) / 1e9,
            "frac_hbm": alg / c.world / (ms * 1e-3) / 1e9 / c.hbm_peak,
-           "bound": "L2-resident gather (16 MiB field): latency / issue, not HBM"}
+           "bound": "L2-resident gather (16 MiB field): latency / issue, not HBM",
+           "order": "map order by SM territories when this rank's share is dense and large enough (>= one pose per 16 map cells "
+                    "and >= 24 M rays: 1 GPU and 2 GPUs here), the caller's order otherwise"}
     if c.dist_on:
         peer = PeerGather(c.local_rank, per * A)
         sp = int(torch.cuda.current_stream(c.local_rank).cuda_stream)
@@ -911,13 +917,13 @@ def config5(c):
     rays = n_total * R
     alg = 4.0 * msteps + 4.0 * rays + 12.0 * n_total
     res = {"workload": f"synth_map({n_map},{seed}) (256 MiB fp32 field, replicated), 16M poses x 270 beams sharded x{c.world}, "
-                       f"marched in {n_chunks_s} pieces of {chunk_s} poses per rank, each piece visited in map order (64 px bins: the "
-                       "field is twice the L2, so the poses in flight are made to share their neighbourhoods)",
+                       f"marched in {n_chunks_s} pieces of {chunk_s} poses per rank, each piece in map order by SM territories "
+                       "(march_territory_kernel: the field is twice the L2, neighbouring poses share their field cells in L1 / L2)",
            "rays": rays, "kernel_ms": ms, "rays_per_s": rays / (ms * 1e-3), "march_steps_per_ray": msteps / rays,
            "algorithmic_bytes": alg, "achieved_gbs": alg / c.world / (ms * 1e-3) / 1e9,
            "frac_hbm": alg / c.world / (ms * 1e-3) / 1e9 / c.hbm_peak, "ingest_ms": omap.ingest_ms,
            "bound": "the one HBM-side case: the field is twice the L2, misses are 32-byte sector gathers from HBM (3.3 TB/s of "
-                    "them in caller order, profiles/r02_cfg35_metrics.csv; map order turns most into L2 hits)"}
+                    "them in caller order, profiles/r02_cfg35_metrics.csv; map order + SM territories turn most into L1 / L2 hits)"}
     if c.dist_on:
         peer = PeerGather(c.local_rank, chunk * R, nbuf=2)
 

@@ -82,7 +82,7 @@ typedef enum rl_status {
 /* Large batches of poses are MARCHED in map order by SM territories: one counting sort of the pose indices by  */
 /* Morton cell per call (scratch from a pool the marcher owns), then every SM works through one contiguous range */
 /* of that order, so neighbouring poses share their field cells in its L1.  Applied when the poses are dense     */
-/* (>= one per 16 map cells and >= 32 M rays) or the field is larger than L2 (>= 16 384 poses and >= 16 M rays). */
+/* (>= one per 16 map cells and >= 24 M rays) or the field is larger than L2 (>= 16 384 poses and >= 16 M rays). */
 /* Poses are read and ranges written at the caller's indices; results are identical.  This flag keeps the       */
 /* caller's order.                                                                                               */
 #define RL_FLAG_NO_POSE_SORT 4u

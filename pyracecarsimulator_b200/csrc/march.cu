@@ -236,7 +236,7 @@ __device__ __forceinline__ uint32_t territory_len(const Territories &T, uint32_t
 // The range with the most unclaimed tasks (all lanes get the same answer), or 0xffffffff when none is left.
 // (Helping in the NEXT range with work left instead -- so that thieves spread out -- measured 5 % slower on uniform
 // poses and 24 % slower on a particle cloud, whose ranges differ a lot in cost: the fullest range is the one that
-// would finish last.)
+// would finish last.  One task per claim with the next claim issued a task ahead: 3-8 % slower than four per claim.)
 __device__ __forceinline__ uint32_t busiest_territory(const Territories &T, unsigned lane)
 {
     uint32_t best_left = 0, best_r = 0xffffffffu;
@@ -573,13 +573,13 @@ int32_t launch_pose(rl_marcher *m, const float *d_poses, int64_t stride_rows, co
     const PeerOut po = peers ? *peers : PeerOut{};
     // large batches are marched in map order, by SM territories (see march_territory_kernel); scratch is stream-ordered
     // Worth it when the poses are dense enough to share field cells (L2-resident field: at least one pose per 16 map
-    // cells and 32 M rays -- 1 M x 60 on a 2049^2 map gains 19 %, 65 536 x 1080 gains 3 %, smaller batches lose to
+    // cells and 24 M rays -- 1 M x 60 on a 2049^2 map gains 19 %, 65 536 x 1080 gains 3 %, smaller batches lose to
     // the sort's ~50 us) or when the field is larger than L2 and locality saves DRAM sector gathers (config 5: +80 %).
     bool by_territories = false;
     if (m->sort_poses && !peers && num_poses < ((int64_t)1 << 32) && blocks * (CTA_THREADS / 32) < ((int64_t)1 << 32)) {
         if (m->sort_forced) by_territories = num_poses >= m->sort_min_poses;
         else if (m->field_beyond_l2) by_territories = num_poses >= 16384 && total >= ((int64_t)16 << 20);
-        else by_territories = num_poses * 16 >= (int64_t)m->P.rows * m->P.cols && total >= ((int64_t)32 << 20);
+        else by_territories = num_poses * 16 >= (int64_t)m->P.rows * m->P.cols && total >= ((int64_t)24 << 20);
     }
     if (by_territories) {
         Territories terr{};
