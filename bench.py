@@ -690,7 +690,7 @@ def run_native(args, rank, world, local_rank):
             line["gather_nccl"] = entry(ms_nccl, "march, then NCCL all_gather_into_tensor of the ranges")
             line["gather_check"] = gather_check
             line["gather_backend"] = c.gather_backend if hasattr(c, "gather_backend") else None
-            line["gather_mode"] = os.environ.get("RL_GATHER_MODE", "mc")
+            line["gather_mode"] = os.environ.get("RL_GATHER_MODE", "auto (peer stores between 2 GPUs, NVLS multicast from 3 up)")
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         if configs is not None:

@@ -420,11 +420,15 @@ pose_sort_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_st
     }
 }
 
-template <bool FAN, bool COUNT, bool SMALL, bool PADDED>
+// PEERS: the fused march + all-gather (OUT_PEERS of march_pose_kernel): every range goes straight to slot `rank` of
+// every GPU's gathered buffer, at the caller's index (4-byte stores: a pose's block of ranges starts on a 4-byte
+// boundary only, and at 8 GPUs the step is bound by NVLink ingress whatever the store width).
+template <bool FAN, bool COUNT, bool SMALL, bool PADDED, bool PEERS>
 __global__ void __launch_bounds__(CTA_THREADS, 2048 / CTA_THREADS)   // 32 registers, like the plain kernel: every warp slot of the SM
 march_territory_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_stride_floats,
                        const float *__restrict__ angles, float *__restrict__ outs, int64_t num_rays_total,
-                       int num_beams, rl::FastDiv div, float fov, float inc, unsigned long long *counter, Territories T)
+                       int num_beams, rl::FastDiv div, float fov, float inc, unsigned long long *counter, Territories T,
+                       PeerOut peers)
 {
     release_dependents();
     const unsigned lane = threadIdx.x & 31;
@@ -458,7 +462,8 @@ march_territory_kernel(MarchParams P, const float *__restrict__ poses, int64_t p
                 }
                 k = __ldg(T.perm + k);
                 const float rng = pose_ray<FAN, COUNT, PADDED>(P, poses + k * pose_stride_floats, angles, j, fov, inc, steps);
-                __stcs(outs + (k * num_beams + j), rng);   // streaming store: the ranges are not read again here
+                if (PEERS) peer_store(peers, k * num_beams + j, rng);
+                else __stcs(outs + (k * num_beams + j), rng);   // streaming store: the ranges are not read again here
             }
         }
     }
@@ -576,7 +581,11 @@ int32_t launch_pose(rl_marcher *m, const float *d_poses, int64_t stride_rows, co
     // cells and 24 M rays -- 1 M x 60 on a 2049^2 map gains 19 %, 65 536 x 1080 gains 3 %, smaller batches lose to
     // the sort's ~50 us) or when the field is larger than L2 and locality saves DRAM sector gathers (config 5: +80 %).
     bool by_territories = false;
-    if (m->sort_poses && !peers && num_poses < ((int64_t)1 << 32) && blocks * (CTA_THREADS / 32) < ((int64_t)1 << 32)) {
+    // With peer output only between two GPUs and plain peer stores: the territory kernel stores 4 bytes at a time, and
+    // multimem.st is bound by the number of stores (config 5's gathered pieces at 4 GPUs: 98.8 Grays/s against 157 for
+    // the plain kernel's 16-byte multimem stores; between 2 GPUs with peer stores 165 against 82).
+    const bool peers_ok = !peers || (m->gather_territories && po.world <= 2 && po.multicast == 0);
+    if (m->sort_poses && peers_ok && num_poses < ((int64_t)1 << 32) && blocks * (CTA_THREADS / 32) < ((int64_t)1 << 32)) {
         if (m->sort_forced) by_territories = num_poses >= m->sort_min_poses;
         else if (m->field_beyond_l2) by_territories = num_poses >= 16384 && total >= ((int64_t)16 << 20);
         else by_territories = num_poses * 16 >= (int64_t)m->P.rows * m->P.cols && total >= ((int64_t)24 << 20);
@@ -630,9 +639,9 @@ int32_t launch_pose(rl_marcher *m, const float *d_poses, int64_t stride_rows, co
                 cfg.numAttrs = 1;
                 RL_CUDA(cudaLaunchKernelEx(&cfg, pose_sort_kernel, m->P, d_poses, stride_floats, terr));
             }
-#define RL_TERR2(COUNT, SMALL, PADDED)                                                                       \
+#define RL_TERR2(COUNT, SMALL, PADDED, PEERS)                                                                \
             do {                                                                                             \
-                auto kern = march_territory_kernel<FAN, COUNT, SMALL, PADDED>;                               \
+                auto kern = march_territory_kernel<FAN, COUNT, SMALL, PADDED, PEERS>;                        \
                 static const int per_sm = [&] {                                                              \
                     int v = 0;                                                                               \
                     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, CTA_THREADS, 0) != cudaSuccess) cudaGetLastError(); \
@@ -641,11 +650,12 @@ int32_t launch_pose(rl_marcher *m, const float *d_poses, int64_t stride_rows, co
                 int64_t grid = (int64_t)per_sm * m->sm_count;                                                \
                 if (grid > blocks) grid = blocks;                                                            \
                 RL_CUDA(launch_windowed_ex(m, kern, (unsigned)grid, s, false, false, m->P, d_poses, stride_floats, d_angles, \
-                                        d_outs, total, num_beams, div, fov, inc, ctr, terr));                \
+                                        d_outs, total, num_beams, div, fov, inc, ctr, terr, po));            \
             } while (0)
-#define RL_TERR(COUNT, SMALL) do { if (m->P.pad > 0) RL_TERR2(COUNT, SMALL, true); else RL_TERR2(COUNT, SMALL, false); } while (0)
-            if (m->count) { if (small) RL_TERR(true, true); else RL_TERR(true, false); }
-            else { if (small) RL_TERR(false, true); else RL_TERR(false, false); }
+#define RL_TERR(COUNT, SMALL, PEERS) do { if (m->P.pad > 0) RL_TERR2(COUNT, SMALL, true, PEERS); else RL_TERR2(COUNT, SMALL, false, PEERS); } while (0)
+            if (peers) { if (small) RL_TERR(false, true, true); else RL_TERR(false, false, true); }
+            else if (m->count) { if (small) RL_TERR(true, true, false); else RL_TERR(true, false, false); }
+            else { if (small) RL_TERR(false, true, false); else RL_TERR(false, false, false); }
 #undef RL_TERR
 #undef RL_TERR2
             cudaFreeAsync(scratch, s);
@@ -888,6 +898,7 @@ int32_t rl_marcher_create(const rl_map *map, float max_range_px, uint32_t flags,
         cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, map->device);
         m->field_beyond_l2 = (m->field_bytes ? m->field_bytes : (size_t)map->rows * map->cols * sizeof(float)) > (size_t)l2_bytes;
         if (const char *e = std::getenv("RL_SORT_SHIFT")) { const int v = std::atoi(e); if (v >= 0 && v <= 12) m->sort_shift = v; }
+        if (const char *e = std::getenv("RL_GATHER_TERRITORIES")) m->gather_territories = e[0] != '0';
         if (const char *e = std::getenv("RL_SORT_MIN_POSES")) { const long v = std::atol(e); if (v >= 1) m->sort_min_poses = v; }
     }
     if (m->sort_poses) {   // stream-ordered scratch for the sort, kept by the pool between calls

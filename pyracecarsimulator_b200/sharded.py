@@ -59,14 +59,17 @@ class PeerGather:
                  backend: str = "auto", multicast: Optional[bool] = None, nbuf: int = 2):
         import os
         from . import _native
-        # RL_GATHER_MODE = mc (NVLS multicast, default) | mc_weak (multimem.st.weak) | uc (one store per peer)
-        gmode = os.environ.get("RL_GATHER_MODE", "mc")
+        # RL_GATHER_MODE = auto | mc (NVLS multicast: multimem.st) | mc_weak (multimem.st.weak) | uc (one store per peer).
+        # auto: multicast from 3 GPUs up.  Between 2 GPUs a multimem.st buys nothing (one remote copy either way) and
+        # the NVLS path moved 17.7 MB in 0.071 ms against 0.044 ms for plain peer stores; config 5's gathered pieces
+        # ran at 92.6 vs 165 Grays/s (profiles/r02_bench_n2*.json).  At 8 GPUs multicast wins (0.226 vs 0.284 ms).
+        gmode = os.environ.get("RL_GATHER_MODE", "auto")
+        self.world = dist.get_world_size(group)
         if multicast is None:
-            multicast = gmode != "uc"
+            multicast = gmode in ("mc", "mc_weak") or (gmode == "auto" and self.world >= 3)
         self._weak = gmode == "mc_weak"
         self._native = _native
         self.group = group
-        self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.device_index = int(device_index)
         self.slot_rays = int(slot_rays)

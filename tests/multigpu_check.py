@@ -73,6 +73,24 @@ def main():
         ok = ok and all(checks)
         if rank == 0:
             print(f"repeat_angles n={n}: nccl={checks[0]} fused={checks[1]}")
+    # the fused gathers through the map-order kernel (march_territory_kernel with peer stores), forced on these sizes
+    os.environ.update({"RL_SORT_POSES": "1", "RL_SORT_MIN_POSES": "1"})
+    rmt = range_libc.PyRayMarchingGPU(omap, 300)
+    for k in ("RL_SORT_POSES", "RL_SORT_MIN_POSES"):
+        os.environ.pop(k, None)
+    sct = ShardedScanner(gpu_march_fn(rmt, fov, R), R, dev)
+    scta = ShardedScanner(gpu_march_angles_fn(rmt, angles), A, dev)
+    for n in (4099, 64, 3):
+        poses = torch.from_numpy(maps.sample_free_poses(omap.dist(), n, 9 + n, y.resolution, y.origin))
+        want = torch.empty(n * R, dtype=torch.float32, device=dev)
+        rm.calc_range_fan(poses.to(dev), want, fov, R)
+        wanta = torch.empty(n * A, dtype=torch.float32, device=dev)
+        rm.calc_range_repeat_angles(poses.to(dev), angles, wanta)
+        checks = [torch.equal(sct.scan_fused(poses, rmt, fov), want), torch.equal(scta.scan_fused(poses, rmt, angles=angles), wanta),
+                  torch.equal(sct.scan(poses, gather="all"), want)]
+        ok = ok and all(checks)
+        if rank == 0:
+            print(f"territories n={n}: fused fan={checks[0]} fused angles={checks[1]} nccl={checks[2]}")
     # back-to-back fused calls: the view of call i stays valid while call i+1 runs (two buffer sets)
     pa = torch.from_numpy(maps.sample_free_poses(omap.dist(), 800, 1, y.resolution, y.origin))
     pb = torch.from_numpy(maps.sample_free_poses(omap.dist(), 800, 2, y.resolution, y.origin))

@@ -294,10 +294,13 @@ def test_territories_on_small_and_ragged_batches(big, n, R):
 
 # --------------------------------------------------------------------------- fused all-gather, repeat_angles + 16-byte stores
 @pytest.mark.parametrize("B,R", [(300, 60), (37, 61), (64, 1080)])
-def test_fused_allgather_repeat_angles_two_virtual_ranks(big, B, R):
+@pytest.mark.parametrize("territories", [False, True], ids=["caller-order", "territories"])
+def test_fused_allgather_repeat_angles_two_virtual_ranks(big, B, R, territories):
     import torch
     from pyracecarsimulator_b200.sharded import _DevicePtr
     L = _native.lib()
+    # territories: the gathered march takes the map-order kernel (forced here whatever the batch size)
+    rm = _marcher_with_env(big["omap"], 300, {"RL_SORT_POSES": "1", "RL_SORT_MIN_POSES": "1"}) if territories else big["rm"]
     slot = B * R + (4 - (B * R) % 4) % 4 if R != 61 else B * R   # R = 61: rank 1's slot is misaligned -> 4-byte stores
     bufs = []
     try:
@@ -311,10 +314,10 @@ def test_fused_allgather_repeat_angles_two_virtual_ranks(big, B, R):
         d_angles = torch.from_numpy(angles).cuda()
         for r in range(2):
             dp = torch.from_numpy(poses[r]).cuda()
-            _native.check(L.rl_calc_range_repeat_angles_allgather(big["rm"]._h, dp.data_ptr(), d_angles.data_ptr(), ptrs,
+            _native.check(L.rl_calc_range_repeat_angles_allgather(rm._h, dp.data_ptr(), d_angles.data_ptr(), ptrs,
                                                                   2, r, slot, B, R, 0, None))
             if R == 1080:   # the fan form through the same 16-byte store path
-                _native.check(L.rl_calc_range_fan_allgather(big["rm"]._h, dp.data_ptr(), 1, ptrs, 2, r, slot, B, R, FOV, 0, None))
+                _native.check(L.rl_calc_range_fan_allgather(rm._h, dp.data_ptr(), 1, ptrs, 2, r, slot, B, R, FOV, 0, None))
         torch.cuda.synchronize()
         for r in range(2):
             got = torch.as_tensor(_DevicePtr(bufs[r].value, 2 * slot), device="cuda").cpu().numpy()

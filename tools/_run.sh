@@ -1,5 +1,12 @@
 mkdir -p gpurun_out
-M=gpu__time_duration.sum,l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_hit.sum,lts__t_sectors_srcunit_tex_op_read.sum,lts__t_sectors_srcunit_tex_op_read_lookup_hit.sum,lts__t_sectors.sum,lts__t_bytes.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,l1tex__m_l1tex2xbar_req_cycles_active.avg.pct_of_peak_sustained_elapsed,l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,lts__throughput.avg.pct_of_peak_sustained_elapsed,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,smsp__thread_inst_executed_per_inst_executed.ratio,launch__grid_size,launch__registers_per_thread
-cd tools
-timeout 900 ncu -k regex:"march|sort" --metrics $M --clock-control none --csv --log-file ../gpurun_out/r2w_territories_ncu.csv python r02_terr_ncu.py > ../gpurun_out/r2w.log 2>&1
-tail -4 ../gpurun_out/r2w.log
+run() { timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 4 --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/$1.json 2> gpurun_out/$1.err; tail -c 200 gpurun_out/$1.err; }
+run r2z_bench_n4
+RL_GATHER_MODE=uc run r2z_bench_n4_uc
+python - <<'PY'
+import json
+for f in ('r2z_bench_n4','r2z_bench_n4_uc'):
+    d=json.loads(open(f'gpurun_out/{f}.json').read().strip().splitlines()[-1])
+    print(f,'value',d['value']/1e9,'ms',d['ms_per_step'], 'stores_only', d['roofline']['nvlink']['stores_only_ms'], 'e2e', d['e2e']['value']/1e9, 'steady', d['steady_state']['value']/1e9, 'sharded', d['sharded']['value']/1e9, 'nccl', d['gather_nccl']['value']/1e9)
+    for k in ('config3','config5','config4'):
+        c=d['configs'][k]; print('  ',k,'sharded',c.get('rays_per_s',c.get('nominal_rays_per_s',0))/1e9, 'with_gather',c.get('with_gather',{}).get('rays_per_s',0)/1e9, c.get('with_gather',{}).get('own_slot_check'), c.get('with_gather',{}).get('check'))
+PY
