@@ -1,13 +1,10 @@
 mkdir -p gpurun_out
-(timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -5) > gpurun_out/r2C_tests.log 2>&1
-tail -5 gpurun_out/r2C_tests.log
-timeout 900 python bench.py --no-cpu-baseline > gpurun_out/r2C_bench_n1.json 2> gpurun_out/r2C_bench_n1.err
-tail -c 300 gpurun_out/r2C_bench_n1.err
-python - <<'PY'
+N=$1
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N > gpurun_out/r2k_bench_n$N.json 2> gpurun_out/r2k_bench_n$N.err; tail -c 200 gpurun_out/r2k_bench_n$N.err
+python - <<PY
 import json
-d=json.loads(open('gpurun_out/r2C_bench_n1.json').read().strip().splitlines()[-1])
-r=d['roofline']
-print('value',d['value']/1e9,'ms',d['ms_per_step'],'kernel',r['kernel_ms'],'warm',r['kernel_ms_warm_l2'],'pinned',r['kernel_ms_flushed_field_pinned'],'steady',d['steady_state']['ms_per_launch'],'so',d['steady_state']['stream_order']['ms_per_launch'],'e2e',d['e2e']['value']/1e9, 'crash', d['e2e_fused_crash']['ms_per_call'])
-for k in ('config1','config3','config4','config5'):
-    c=d['configs'][k]; print(k,{x:c[x] for x in c if x in('kernel_ms','rays_per_s','us_per_scan','nominal_rays_per_s')})
+d=json.loads(open('gpurun_out/r2k_bench_n$N.json').read().strip().splitlines()[-1])
+print('value',d['value']/1e9,'ms',d['ms_per_step'], 'stores_only', d['roofline']['nvlink']['stores_only_ms'], 'e2e', d['e2e']['value']/1e9, 'steady', d['steady_state']['value']/1e9, 'sharded', d['sharded']['value']/1e9, d['sharded']['ms_per_step'], 'nccl', d['gather_nccl']['value']/1e9, d['gather_nccl']['ms_per_step'], d.get('gather_check'), d.get('gather_mode'))
+for k in ('config3','config5','config4'):
+    c=d['configs'][k]; print('  ',k,'sharded',c.get('rays_per_s',c.get('nominal_rays_per_s',0))/1e9, 'with_gather',c.get('with_gather',{}).get('rays_per_s',0)/1e9, c.get('with_gather',{}).get('own_slot_check'), c.get('with_gather',{}).get('check'))
 PY
