@@ -4,7 +4,7 @@
 // scripts/ros_interface.py:80-86, :210 and scripts/scan_simulator.py:72-76).
 //
 // Kernels (north_star (a): column pass + row pass):
-//   edt_classify_kernel  one thread per (column, 64-row segment): classifies every source cell
+//   edt_classify_kernel  one thread per (column, 32-row segment): classifies every source cell
 //                    through a 256-entry bit LUT (map_server thresholds / binarisation / `> 10`
 //                    cut are all pure functions of one byte, so the host folds them into the LUT
 //                    with the reference's double arithmetic), applies map_server's y-flip, writes
@@ -16,7 +16,9 @@
 //                    envelope min_k (k^2 + g^2[q +- k]), by an outward scan that stops at k^2 >= best
 //                    when the row's cost bound is small and by divide and conquer over the monotone
 //                    argmin (O(W log W) per row whatever the map) otherwise; exact in integers either
-//                    way; writes d^2 (int32) and sqrt_rn((float)d^2).
+//                    way; writes d^2 (int32) and sqrt_rn((float)d^2).  The scan stages the row unpadded (consecutive
+//                    threads read consecutive words, the offsets of a trip are immediates of one address) and needs
+//                    no clamping while both neighbours are inside the row: 88 -> 64 us on the 2049^2 stand-in.
 // For max(rows, cols) <= 2896 the reference's float Felzenszwalb transform returns exactly
 // this integer d^2, so the fp32 field is bit-identical to the reference's.
 #include <cmath>
@@ -37,7 +39,7 @@ __device__ __forceinline__ uint32_t lut_bit(const ByteLut &lut, uint32_t p)
     return (lut.w[p >> 5] >> (p & 31u)) & 1u;
 }
 
-constexpr int SEG_ROWS = 64;   // rows per column segment: W * ceil(H/64) threads instead of W
+constexpr int SEG_ROWS = 32;   // rows per column segment: W * ceil(H/32) threads instead of W
 constexpr int SEG_NONE_LAST = -1;
 constexpr int SEG_NONE_FIRST = 0x3fffffff;
 
@@ -52,7 +54,7 @@ edt_classify_kernel(const uint8_t *__restrict__ src, int rows, int cols, int fli
     if (c >= cols) return;
     const int r0 = seg * SEG_ROWS, r1 = min(rows, r0 + SEG_ROWS);
     int first = SEG_NONE_FIRST, last = SEG_NONE_LAST;
-#pragma unroll 8
+#pragma unroll 16
     for (int r = r0; r < r1; ++r) {
         const int sr = flip ? rows - 1 - r : r;
         const uint32_t o = lut_bit(lut, src[(size_t)sr * cols + c]);
@@ -142,13 +144,13 @@ edt_cols_kernel(const uint8_t *__restrict__ occ, int rows, int cols, int nseg,
     const int r0 = seg * SEG_ROWS, r1 = min(rows, r0 + SEG_ROWS);
     const int above = seg_above[(size_t)seg * cols + c], below = seg_below[(size_t)seg * cols + c];
     uint32_t run = (above == SEG_NONE_LAST) ? G_INF : min((uint32_t)(r0 - 1 - above), G_INF);
-#pragma unroll 8
+#pragma unroll 16
     for (int r = r0; r < r1; ++r) {
         run = occ[(size_t)r * cols + c] ? 0u : min(run + 1u, G_INF);
         g[(size_t)r * cols + c] = (uint16_t)run;
     }
     run = (below == SEG_NONE_FIRST) ? G_INF : min((uint32_t)(below - r1), G_INF);
-#pragma unroll 8
+#pragma unroll 16
     for (int r = r1 - 1; r >= r0; --r) {
         const uint32_t gv = g[(size_t)r * cols + c];
         run = (gv == 0u) ? 0u : min(run + 1u, G_INF);
@@ -206,13 +208,13 @@ edt_rows_kernel(const uint16_t *__restrict__ g, int rows, int cols, int log2T, i
     const uint16_t *grow = g + (size_t)r * cols;
     if (tid == 0) cost = 0;
     __syncthreads();
+    // first look at the row: is any column within reach of an obstacle, and what would the outward scan cost?
     bool any_near = false;
     uint32_t mine = 0;
     for (int q = tid; q < cols; q += ROW_THREADS) {
         const uint32_t v = grow[q];
         any_near |= v < G_INF;
         mine += min(v, (uint32_t)cols);
-        g2[sw(q)] = (v >= G_INF) ? G2_FAR : v * v;
     }
     mine = __reduce_add_sync(0xffffffffu, mine);
     if ((tid & 31) == 0) atomicAdd(&cost, (unsigned long long)mine);
@@ -229,22 +231,44 @@ edt_rows_kernel(const uint16_t *__restrict__ g, int rows, int cols, int log2T, i
     }
     const bool scan = force == ROWS_SCAN || (force == ROWS_AUTO && cost <= (unsigned long long)budget * cols);
     if (scan) {
-        // Out-of-row neighbours are clamped to the row ends: the clamped candidate k^2 + g2[end] is never below
-        // the true candidate (q - end)^2 + g2[end], so the minimum is unchanged.  Four offsets per trip
-        // (independent shared-memory loads, one exit test).
+        // The scan reads g2[q - k] and g2[q + k] for consecutive q: the row is staged UNPADDED (g2[q]), consecutive
+        // threads read consecutive words and the four offsets of a trip are immediate offsets of one address.  (The
+        // second read of the row comes from L1 / L2.)
+        for (int q = tid; q < cols; q += ROW_THREADS) {
+            const uint32_t v = grow[q];
+            g2[q] = (v >= G_INF) ? G2_FAR : v * v;
+        }
+        __syncthreads();
         const int last = cols - 1;
         for (int q = tid; q < cols; q += ROW_THREADS) {
-            uint32_t best = g2[sw(q)];
-            const int reach = max(q, last - q);
-            for (int k = 1; k <= reach; k += 4) {
+            uint32_t best = g2[q];
+            const int both = min(q, last - q), reach = max(q, last - q);
+            int k = 1;
+            // both neighbours inside the row: no clamping.  Four offsets per trip (independent loads, one exit test).
+            for (; k + 3 <= both; k += 4) {
+                if ((uint32_t)k * (uint32_t)k >= best) break;
+                const uint32_t *lo = g2 + (q - k), *hi = g2 + (q + k);
+                uint32_t c[8];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t k2 = (uint32_t)(k + u) * (uint32_t)(k + u);
+                    c[2 * u] = k2 + lo[-u];
+                    c[2 * u + 1] = k2 + hi[u];
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) best = min(best, c[u]);
+            }
+            // the rest (one side has left the row): out-of-row neighbours are clamped to the row ends -- the clamped
+            // candidate k^2 + g2[end] is never below the true candidate (q - end)^2 + g2[end], so the minimum is unchanged
+            for (; k <= reach; k += 4) {
                 if ((uint32_t)k * (uint32_t)k >= best) break;
                 uint32_t c[8];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int kk = k + u;
                     const uint32_t k2 = (uint32_t)kk * (uint32_t)kk;
-                    c[2 * u] = k2 + g2[sw(max(q - kk, 0))];
-                    c[2 * u + 1] = k2 + g2[sw(min(q + kk, last))];
+                    c[2 * u] = k2 + g2[max(q - kk, 0)];
+                    c[2 * u + 1] = k2 + g2[min(q + kk, last)];
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) best = min(best, c[u]);
@@ -262,6 +286,13 @@ edt_rows_kernel(const uint16_t *__restrict__ g, int rows, int cols, int log2T, i
         }
         return;
     }
+    // divide and conquer: the row staged with one padding word per 32 (sw()), so that the power-of-two strides of the
+    // bisection order do not pile onto one bank
+    for (int q = tid; q < cols; q += ROW_THREADS) {
+        const uint32_t v = grow[q];
+        g2[sw(q)] = (v >= G_INF) ? G2_FAR : v * v;
+    }
+    __syncthreads();
     for (int h = 1 << (log2T - 1); h >= 1; h >>= 1) {
         const int nq = (cols / h + 1) >> 1;   // queries of this level: (2j+1) h <= cols
         if (nq > ROW_THREADS / 32) {          // a query per thread (several per thread at the bottom levels)

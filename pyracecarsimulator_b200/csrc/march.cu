@@ -618,8 +618,8 @@ int32_t launch_pose(rl_marcher *m, const float *d_poses, int64_t stride_rows, co
             terr.tasks_per_range = (terr.n_tasks + terr.n_ranges - 1) / terr.n_ranges;
             // whole claims per range, so that only a range's last claim can be short
             terr.tasks_per_range = (terr.tasks_per_range + TERR_CLAIM - 1) / TERR_CLAIM * TERR_CLAIM;
-            RL_CUDA(cudaMemsetAsync(scratch, 0, zero_b, s));
-            {
+            bool sorted = cudaMemsetAsync(scratch, 0, zero_b, s) == cudaSuccess;
+            if (sorted) {
                 static const int sort_per_sm = [] {
                     int v = 0;
                     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, pose_sort_kernel, SORT_THREADS, 0) != cudaSuccess) cudaGetLastError();
@@ -637,8 +637,21 @@ int32_t launch_pose(rl_marcher *m, const float *d_poses, int64_t stride_rows, co
                 attr[0].val.cooperative = 1;
                 cfg.attrs = attr;
                 cfg.numAttrs = 1;
-                RL_CUDA(cudaLaunchKernelEx(&cfg, pose_sort_kernel, m->P, d_poses, stride_floats, terr));
+                sorted = cudaLaunchKernelEx(&cfg, pose_sort_kernel, m->P, d_poses, stride_floats, terr) == cudaSuccess;
             }
+            if (!sorted) {   // e.g. no room for a cooperative launch: the caller's order will do
+                cudaGetLastError();
+                cudaFreeAsync(scratch, s);
+                scratch = nullptr;
+            }
+#define RL_TERR_FAIL(expr)                                                                                   \
+            do {                                                                                             \
+                const cudaError_t e_ = (expr);                                                               \
+                if (e_ != cudaSuccess) {                                                                     \
+                    cudaFreeAsync(scratch, s);                                                               \
+                    return rl::fail(RL_ERR_CUDA, std::string("march_territory_kernel: ") + cudaGetErrorString(e_)); \
+                }                                                                                            \
+            } while (0)
 #define RL_TERR2(COUNT, SMALL, PADDED, PEERS)                                                                \
             do {                                                                                             \
                 auto kern = march_territory_kernel<FAN, COUNT, SMALL, PADDED, PEERS>;                        \
@@ -649,18 +662,21 @@ int32_t launch_pose(rl_marcher *m, const float *d_poses, int64_t stride_rows, co
                 }();                                                                                         \
                 int64_t grid = (int64_t)per_sm * m->sm_count;                                                \
                 if (grid > blocks) grid = blocks;                                                            \
-                RL_CUDA(launch_windowed_ex(m, kern, (unsigned)grid, s, false, false, m->P, d_poses, stride_floats, d_angles, \
-                                        d_outs, total, num_beams, div, fov, inc, ctr, terr, po));            \
+                RL_TERR_FAIL(launch_windowed_ex(m, kern, (unsigned)grid, s, false, false, m->P, d_poses, stride_floats, d_angles, \
+                                                d_outs, total, num_beams, div, fov, inc, ctr, terr, po));    \
             } while (0)
 #define RL_TERR(COUNT, SMALL, PEERS) do { if (m->P.pad > 0) RL_TERR2(COUNT, SMALL, true, PEERS); else RL_TERR2(COUNT, SMALL, false, PEERS); } while (0)
-            if (peers) { if (small) RL_TERR(false, true, true); else RL_TERR(false, false, true); }
-            else if (m->count) { if (small) RL_TERR(true, true, false); else RL_TERR(true, false, false); }
-            else { if (small) RL_TERR(false, true, false); else RL_TERR(false, false, false); }
+            if (sorted) {
+                if (peers) { if (small) RL_TERR(false, true, true); else RL_TERR(false, false, true); }
+                else if (m->count) { if (small) RL_TERR(true, true, false); else RL_TERR(true, false, false); }
+                else { if (small) RL_TERR(false, true, false); else RL_TERR(false, false, false); }
+                cudaFreeAsync(scratch, s);
+                RL_CUDA(cudaGetLastError());
+                return RL_OK;
+            }
 #undef RL_TERR
 #undef RL_TERR2
-            cudaFreeAsync(scratch, s);
-            RL_CUDA(cudaGetLastError());
-            return RL_OK;
+#undef RL_TERR_FAIL
         }
         cudaGetLastError();   // no scratch: march in the caller's order
     }

@@ -1,10 +1,15 @@
 mkdir -p gpurun_out
-N=$1
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N > gpurun_out/r2k_bench_n$N.json 2> gpurun_out/r2k_bench_n$N.err; tail -c 200 gpurun_out/r2k_bench_n$N.err
-python - <<PY
-import json
-d=json.loads(open('gpurun_out/r2k_bench_n$N.json').read().strip().splitlines()[-1])
-print('value',d['value']/1e9,'ms',d['ms_per_step'], 'stores_only', d['roofline']['nvlink']['stores_only_ms'], 'e2e', d['e2e']['value']/1e9, 'steady', d['steady_state']['value']/1e9, 'sharded', d['sharded']['value']/1e9, d['sharded']['ms_per_step'], 'nccl', d['gather_nccl']['value']/1e9, d['gather_nccl']['ms_per_step'], d.get('gather_check'), d.get('gather_mode'))
-for k in ('config3','config5','config4'):
-    c=d['configs'][k]; print('  ',k,'sharded',c.get('rays_per_s',c.get('nominal_rays_per_s',0))/1e9, 'with_gather',c.get('with_gather',{}).get('rays_per_s',0)/1e9, c.get('with_gather',{}).get('own_slot_check'), c.get('with_gather',{}).get('check'))
-PY
+(timeout 1500 python -m pytest tests/test_gpu_ingest.py tests/test_gpu_fuzz.py tests/test_gpu_round2.py -x -q 2>&1 | tail -4)
+timeout 900 python tools/r02_probe.py edt 2> gpurun_out/r2m_edt.err | python -c "
+import sys,json
+for l in sys.stdin:
+    d=json.loads(l); print(d['map'], {k:round(v,3) for k,v in d.items() if k.endswith('_ms') and 'budget' not in k})
+"
+tail -2 gpurun_out/r2m_edt.err
+cd tools && timeout 300 ncu -k regex:edt --metrics gpu__time_duration.sum --clock-control none --csv --log-file ../gpurun_out/r2m_edt_ncu.csv python -c "
+import sys, os
+sys.path.insert(0, os.path.dirname(os.getcwd()))
+from r02_probe import config2
+import torch
+config2(); torch.cuda.synchronize()
+" > /dev/null 2>&1; grep -v "^==" ../gpurun_out/r2m_edt_ncu.csv | cut -d, -f5,15 | cut -c1-50,60- | tail -6
