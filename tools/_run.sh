@@ -1,15 +1,9 @@
 mkdir -p gpurun_out
-(timeout 1500 python -m pytest tests/test_gpu_ingest.py tests/test_gpu_fuzz.py tests/test_gpu_round2.py -x -q 2>&1 | tail -4)
-timeout 900 python tools/r02_probe.py edt 2> gpurun_out/r2m_edt.err | python -c "
-import sys,json
-for l in sys.stdin:
-    d=json.loads(l); print(d['map'], {k:round(v,3) for k,v in d.items() if k.endswith('_ms') and 'budget' not in k})
-"
-tail -2 gpurun_out/r2m_edt.err
-cd tools && timeout 300 ncu -k regex:edt --metrics gpu__time_duration.sum --clock-control none --csv --log-file ../gpurun_out/r2m_edt_ncu.csv python -c "
+cd tools && timeout 300 ncu -k regex:edt --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed --clock-control none --csv --log-file ../gpurun_out/r2n_edt_ncu.csv python -c "
 import sys, os
 sys.path.insert(0, os.path.dirname(os.getcwd()))
-from r02_probe import config2
 import torch
-config2(); torch.cuda.synchronize()
-" > /dev/null 2>&1; grep -v "^==" ../gpurun_out/r2m_edt_ncu.csv | cut -d, -f5,15 | cut -c1-50,60- | tail -6
+from pyracecarsimulator_b200 import maps, range_libc
+img = maps.synth_map(8192, 5678); y = maps.synth_yaml(8192); p='/tmp/_x.pgm'; maps.write_pgm(p, img); y.image = p
+om = range_libc.PyOMap(y); torch.cuda.synchronize(); print(om.ingest_ms)
+" 2>&1 | tail -2
