@@ -9,6 +9,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:marc
 (cd tools && timeout 600 ncu --set full --clock-control none --import-source on -k regex:"territory|pose_sort" -c 2 -o ../gpurun_out/r2k_territory python r02_terr_ncu.py > ../gpurun_out/r2k_ncu4.log 2>&1)
 timeout 900 python bench.py > gpurun_out/r2k_bench_n1.json 2> gpurun_out/r2k_bench_n1.err
 timeout 600 python bench.py --impl reference > gpurun_out/r2k_bench_ref.json 2> gpurun_out/r2k_bench_ref.err
+timeout 600 python tools/r02_probe.py edt > gpurun_out/r2k_probe_edt.jsonl 2> gpurun_out/r2k_probe_edt.err
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2k_smoke.log 2>&1
 (timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_round2.py tests/test_gpu_march.py tests/test_gpu_car.py -x -q -k "not full_size and not sparse_large and not l2_carve" 2>&1 | tail -15) > gpurun_out/r2k_memcheck.log 2>&1
 tail -5 gpurun_out/r2k_tests.log
