@@ -292,6 +292,34 @@ def test_territories_on_small_and_ragged_batches(big, n, R):
     assert srt.last_steps() == plain.last_steps()
 
 
+def test_map_order_path_is_cuda_graph_capturable(big):
+    """Sort scratch comes from a stream-ordered pool, the sort is one cooperative launch: a batch marched by
+    territories can be captured into a CUDA graph and replayed like the plain march."""
+    import torch
+    n, R = 3000, 61
+    srt = _marcher_with_env(big["omap"], 300, {"RL_SORT_POSES": "1", "RL_SORT_MIN_POSES": "1"})
+    plain = range_libc.PyRayMarchingGPU(big["omap"], 300, flags=_native.RL_FLAG_NO_POSE_SORT)
+    batches = [torch.from_numpy(maps.sample_free_poses(big["dist"], n, 900 + i, big["res"], big["origin"])).cuda() for i in range(3)]
+    dp = batches[0].clone()
+    out = torch.zeros(n * R, dtype=torch.float32, device="cuda")
+    want = torch.zeros_like(out)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                       # warm-up outside capture
+        srt.calc_range_fan(dp, out, FOV, R)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        srt.calc_range_fan(dp, out, FOV, R)
+    for b in batches:                                   # replay on new poses in the captured buffers
+        dp.copy_(b)
+        out.fill_(-1.0)
+        g.replay()
+        plain.calc_range_fan(b, want, FOV, R)
+        torch.cuda.synchronize()
+        assert torch.equal(out, want)
+
+
 # --------------------------------------------------------------------------- fused all-gather, repeat_angles + 16-byte stores
 @pytest.mark.parametrize("B,R", [(300, 60), (37, 61), (64, 1080)])
 @pytest.mark.parametrize("territories", [False, True], ids=["caller-order", "territories"])

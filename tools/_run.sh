@@ -1,5 +1,1 @@
-mkdir -p gpurun_out
-M=gpu__time_duration.sum,l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_hit.sum,lts__t_sectors_srcunit_tex_op_read.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,l1tex__m_l1tex2xbar_req_cycles_active.avg.pct_of_peak_sustained_elapsed,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__thread_inst_executed_per_inst_executed.ratio,smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio,smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_wait_per_issue_active.ratio,smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio,smsp__average_warps_issue_stalled_membar_per_issue_active.ratio,launch__grid_size,launch__registers_per_thread
-cd tools
-timeout 600 ncu --metrics $M --clock-control none --csv --log-file ../gpurun_out/r2o_cfg4_ncu.csv python r02_cfg4_ncu.py > ../gpurun_out/r2o_cfg4.log 2>&1
-tail -2 ../gpurun_out/r2o_cfg4.log
+(timeout 900 python -m pytest tests/test_gpu_round2.py -x -q -k "graph_capturable" 2>&1 | tail -15)
