@@ -736,8 +736,17 @@ int32_t host_pipeline(rl_marcher *m, const float *ins, int64_t in_stride_floats,
         if (out_pinned && zero_copy_ok && rl::host_registered_range(outs, (size_t)units * out_floats * sizeof(float)) == 0) {
             float *d_alias = nullptr;
             if (cudaHostGetDevicePointer((void **)&d_alias, outs + b * out_floats, 0) == cudaSuccess && d_alias) {
-                RL_CUDA(cudaMemcpyAsync(m->d_in, src, (size_t)c * in_floats * sizeof(float), cudaMemcpyHostToDevice, st[0]));
-                rc = launch(0, c, m->d_in, d_alias, st[0]);
+                // a handful of poses (the single scan of the 50 ms tick): the kernel reads them from the page-locked
+                // staging buffer itself -- one API call and one DMA round trip less than copying 12 bytes first
+                const float *d_src = m->d_in;
+                float *mapped = nullptr;
+                if ((size_t)c * in_floats <= 256 && cudaHostGetDevicePointer((void **)&mapped, const_cast<float *>(src), 0) == cudaSuccess && mapped)
+                    d_src = mapped;
+                else {
+                    cudaGetLastError();
+                    RL_CUDA(cudaMemcpyAsync(m->d_in, src, (size_t)c * in_floats * sizeof(float), cudaMemcpyHostToDevice, st[0]));
+                }
+                rc = launch(0, c, d_src, d_alias, st[0]);
                 if (rc != RL_OK) return rc;
                 RL_CUDA(cudaStreamSynchronize(st[0]));
                 continue;
