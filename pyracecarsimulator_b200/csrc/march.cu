@@ -460,7 +460,7 @@ march_territory_kernel(MarchParams P, const float *__restrict__ poses, int64_t p
                     k = i / num_beams;
                     j = (int)(i - k * num_beams);
                 }
-                k = __ldg(T.perm + k);
+                if (T.perm) k = __ldg(T.perm + k);   // null: the caller's order by territories (RL_TERRITORY_IDENTITY, measurements)
                 const float rng = pose_ray<FAN, COUNT, PADDED>(P, poses + k * pose_stride_floats, angles, j, fov, inc, steps);
                 if (PEERS) peer_store(peers, k * num_beams + j, rng);
                 else __stcs(outs + (k * num_beams + j), rng);   // streaming store: the ranges are not read again here
@@ -619,7 +619,8 @@ int32_t launch_pose(rl_marcher *m, const float *d_poses, int64_t stride_rows, co
             // whole claims per range, so that only a range's last claim can be short
             terr.tasks_per_range = (terr.tasks_per_range + TERR_CLAIM - 1) / TERR_CLAIM * TERR_CLAIM;
             bool sorted = cudaMemsetAsync(scratch, 0, zero_b, s) == cudaSuccess;
-            if (sorted) {
+            if (m->territory_identity) terr.perm = nullptr;
+            else if (sorted) {
                 static const int sort_per_sm = [] {
                     int v = 0;
                     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, pose_sort_kernel, SORT_THREADS, 0) != cudaSuccess) cudaGetLastError();
@@ -924,6 +925,7 @@ int32_t rl_marcher_create(const rl_map *map, float max_range_px, uint32_t flags,
         m->field_beyond_l2 = (m->field_bytes ? m->field_bytes : (size_t)map->rows * map->cols * sizeof(float)) > (size_t)l2_bytes;
         if (const char *e = std::getenv("RL_SORT_SHIFT")) { const int v = std::atoi(e); if (v >= 0 && v <= 12) m->sort_shift = v; }
         if (const char *e = std::getenv("RL_GATHER_TERRITORIES")) m->gather_territories = e[0] != '0';
+        if (const char *e = std::getenv("RL_TERRITORY_IDENTITY")) m->territory_identity = e[0] == '1';
         if (const char *e = std::getenv("RL_SORT_MIN_POSES")) { const long v = std::atol(e); if (v >= 1) m->sort_min_poses = v; }
     }
     if (m->sort_poses) {   // stream-ordered scratch for the sort, kept by the pool between calls

@@ -16,6 +16,7 @@ struct rl_marcher {
     bool sort_poses = false;
     bool sort_forced = false;     // RL_SORT_POSES=1: every batch of at least sort_min_poses poses (tests, measurements)
     bool field_beyond_l2 = false;
+    bool territory_identity = false;   // RL_TERRITORY_IDENTITY=1: territories over the caller's order, no sort (measurements)
     bool gather_territories = true;   // the fused march + all-gather between 2 GPUs (plain peer stores) takes the territory kernel too (RL_GATHER_TERRITORIES=0: never)
     int sort_shift = 4;           // Morton cells of at least 16 x 16 px (larger when the map has more than 256 of them a side)
     int64_t sort_min_poses = 1;

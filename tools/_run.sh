@@ -1,17 +1,5 @@
-(timeout 900 python -m pytest tests/test_gpu_scan_simulator.py tests/test_gpu_march.py -x -q 2>&1 | tail -3)
-python - <<'PY'
-import os, time, numpy as np
-from pyracecarsimulator_b200 import maps, range_libc
-from pyracecarsimulator_b200.scan_simulator import ScanSimulator2D
-z = np.load("tests/golden/colombia_map.npz")
-maps.write_pgm("/tmp/_c.pgm", z["img"])
-yc = maps.MapYaml("/tmp/_c.pgm", float(z["resolution"]), tuple(float(v) for v in z["origin"]))
-omap = range_libc.PyOMap(yc)
-sim = ScanSimulator2D(1080, 4.71, 0.01, batch_size=200)
-sim.setMap(omap, 300, yc.resolution, yc.origin); sim.setRaytracingMethod("RMGPU")
-for rep in range(3):
-    for _ in range(50): sim.scan(0.275, 0.0, 0.0)
-    t0 = time.perf_counter()
-    for _ in range(1000): sim.scan(0.275, 0.0, 0.0)
-    print("us per scan", (time.perf_counter() - t0) / 1000 * 1e6)
-PY
+mkdir -p gpurun_out
+cd tools
+timeout 600 python r02_cfg2_terr_ncu.py 2>&1 | grep "single"
+M=gpu__time_duration.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_hit.sum,lts__t_sectors_srcunit_tex_op_read.sum,smsp__inst_executed.sum,l1tex__m_l1tex2xbar_req_cycles_active.avg.pct_of_peak_sustained_elapsed,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__thread_inst_executed_per_inst_executed.ratio,launch__grid_size
+timeout 600 ncu -k regex:"territory" -c 2 --metrics $M --clock-control none --csv --log-file ../gpurun_out/r2p_cfg2_terr_ncu.csv python r02_cfg2_terr_ncu.py > /dev/null 2>&1
