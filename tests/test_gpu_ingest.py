@@ -57,7 +57,10 @@ def test_synthetic_maps_bit_exact(orc, n, seed):
 @pytest.mark.parametrize("shape,density,seed", [((1, 1), 1.0, 0), ((1, 1), 0.0, 0), ((1, 300), 0.05, 1),
                                                 ((300, 1), 0.05, 2), ((33, 65), 0.5, 3),
                                                 ((64, 64), 0.0, 4), ((64, 64), 1.0, 5),
-                                                ((257, 129), 0.0005, 6), ((70, 1030), 0.002, 7)])
+                                                ((257, 129), 0.0005, 6), ((70, 1030), 0.002, 7),
+                                                # widths that are multiples of 4 (rows start on 4-byte boundaries)
+                                                ((1, 4), 0.5, 8), ((37, 4), 0.2, 9), ((95, 8), 0.1, 10), ((33, 516), 0.01, 11),
+                                                ((130, 1024), 0.001, 12), ((64, 128), 0.0, 13), ((31, 2052), 0.3, 14)])
 def test_edge_case_grids(orc, shape, density, seed):
     rng = np.random.default_rng(seed)
     occ = (rng.random(shape) < density).astype(np.uint8)

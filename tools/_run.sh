@@ -1,5 +1,8 @@
 mkdir -p gpurun_out
-cd tools
-timeout 600 python r02_cfg2_terr_ncu.py 2>&1 | grep "single"
-M=gpu__time_duration.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_hit.sum,lts__t_sectors_srcunit_tex_op_read.sum,smsp__inst_executed.sum,l1tex__m_l1tex2xbar_req_cycles_active.avg.pct_of_peak_sustained_elapsed,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__thread_inst_executed_per_inst_executed.ratio,launch__grid_size
-timeout 600 ncu -k regex:"territory" -c 2 --metrics $M --clock-control none --csv --log-file ../gpurun_out/r2p_cfg2_terr_ncu.csv python r02_cfg2_terr_ncu.py > /dev/null 2>&1
+(timeout 1500 python -m pytest tests/test_gpu_ingest.py tests/test_gpu_fuzz.py tests/test_gpu_round2.py tests/test_gpu_configs.py tests/test_gpu_scan_simulator.py -x -q 2>&1 | tail -4)
+timeout 900 python tools/r02_probe.py edt > gpurun_out/r2q_probe_edt.jsonl 2> gpurun_out/r2q_edt.err
+python -c "
+import json
+for l in open('gpurun_out/r2q_probe_edt.jsonl'):
+    d=json.loads(l); print(d['map'], {k:round(v,3) for k,v in d.items() if k.endswith('_ms') and 'budget' not in k})
+"
