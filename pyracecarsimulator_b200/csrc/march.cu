@@ -142,8 +142,7 @@ march_pose_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_s
             k = k32;
             j = (int)((uint32_t)i - k32 * (uint32_t)num_beams);
         } else {
-            k = i / num_beams;
-            j = (int)(i - k * num_beams);
+            k = rl::wide_div(i, num_beams, j);
         }
         const float r = pose_ray<FAN, COUNT, PADDED>(P, poses + k * pose_stride_floats, angles, j, fov, inc, steps);
         if (OUT == OUT_PEERS) peer_store(peers, i, r);
@@ -457,8 +456,7 @@ march_territory_kernel(MarchParams P, const float *__restrict__ poses, int64_t p
                     k = k32;
                     j = (int)((uint32_t)i - k32 * (uint32_t)num_beams);
                 } else {
-                    k = i / num_beams;
-                    j = (int)(i - k * num_beams);
+                    k = rl::wide_div(i, num_beams, j);
                 }
                 if (T.perm) k = __ldg(T.perm + k);   // null: the caller's order by territories (RL_TERRITORY_IDENTITY, measurements)
                 const float rng = pose_ray<FAN, COUNT, PADDED>(P, poses + k * pose_stride_floats, angles, j, fov, inc, steps);

@@ -135,4 +135,17 @@ struct FastDiv {
 
 __device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv &f) { return __umulhi(n, f.magic) >> f.shift; }
 
+// n / d for ray indices beyond 2^31 (one call with more than 2 G rays): the quotient of the double-precision
+// product is off by at most one for n < 2^52, one comparison each way puts it right -- a dozen instructions
+// instead of the ~80 of a 64-bit integer division (config 5 in one 4.32 G-ray call: 44.3 -> 43.6 ms).
+__device__ __forceinline__ int64_t wide_div(int64_t n, int d, int &rem)
+{
+    int64_t q = (int64_t)__double2ll_rz(__dmul_rn((double)n, __drcp_rn((double)d)));
+    int64_t r = n - q * d;
+    if (r < 0) { --q; r += d; }
+    if (r >= d) { ++q; r -= d; }
+    rem = (int)r;
+    return q;
+}
+
 }  // namespace rl
