@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-timeout 900 python tools/r02_cfg5_one_call.py 2> gpurun_out/r2s_cfg5.err | tee gpurun_out/r2s_cfg5_one_call.jsonl
-tail -3 gpurun_out/r2s_cfg5.err
+timeout 600 python tools/r02_gate_probe.py 2>/dev/null | grep gate | tee gpurun_out/r2t_gate.jsonl
