@@ -626,6 +626,7 @@ def run_native(args, rank, world, local_rank):
     configs = None
     if not args.no_configs:
         c.flush = flush
+        c.sm_mhz = clocks.get("sm_mhz")
         configs = run_configs(c)
 
     if rank == 0:
@@ -724,6 +725,35 @@ def median_ms(c, fn, reps=3, warm=1, flush=True):
     return c.reduce_max([float(np.median(ts))])[0]
 
 
+def counter_views(c, cfg_key, launches, ms):
+    """Issue / SM->L2 request / DRAM views of a config at N = 1: ncu counters of one launch of this shape
+    (profiles/traffic_configs.json, by territories, sort included) x `launches`, over the time measured here."""
+    path = os.path.join(ROOT, "profiles", "traffic_configs.json")
+    if c.world != 1 or not os.path.exists(path):
+        return None
+    tj = json.load(open(path)).get(cfg_key)
+    if not tj:
+        return None
+    torch = c.torch
+    sms = torch.cuda.get_device_properties(c.local_rank).multi_processor_count
+    mhz = float(getattr(c, "sm_mhz", 0.0) or 1965.0)   # the SM clock sampled under load in the timed region of this run
+    t, srt, plain = tj["territories"], tj["sort"], tj["caller_order"]
+    insts = (t["warp_insts"] + srt["warp_insts"]) * launches
+    l2 = (t["l2_read_sectors_from_sm"] + srt["l2_read_sectors_from_sm"]) * launches
+    dram = (t["dram_bytes_read"] + t["dram_bytes_written"] + srt["dram_bytes_read"] + srt["dram_bytes_written"]) * launches
+    sec = ms * 1e-3
+    return {"issue_frac": insts / sec / (4 * sms * mhz * 1e6), "sm_to_l2_request_frac": l2 / sec / (sms * mhz * 1e6),
+            "dram_gbs": dram / sec / 1e9, "dram_frac": dram / sec / 1e9 / c.hbm_peak,
+            "l1_hit_rate": t["l1_sector_hits"] / t["l1_sectors_requested"],
+            "l1_hit_rate_callers_order": plain["l1_sector_hits"] / plain["l1_sectors_requested"],
+            "dram_bytes_per_launch": {"territories": t["dram_bytes_read"] + t["dram_bytes_written"],
+                                      "callers_order": plain["dram_bytes_read"] + plain["dram_bytes_written"]},
+            "sm_clock_mhz": mhz,
+            "note": "per-launch ncu counters of the map-order path (profiles/traffic_configs.json, from profiles/r02_territories_ncu.csv) "
+                    "over the time measured in this run; issue = 4 warp instructions per SM per clock, SM->L2 = one sector per SM per "
+                    "clock (DESIGN.md 4a): the kernel is issue-bound once its field cells come from L1"}
+
+
 def run_configs(c):
     out = {"note": "BASELINE.json configs at their stated shapes; total work fixed and sharded over the N GPUs (strong "
                    "scaling), device time = median of 3 after a warm-up, max over ranks; algorithmic bytes = 4 B per march "
@@ -794,6 +824,9 @@ def config3(c):
            "bound": "L2-resident gather (16 MiB field): latency / issue, not HBM",
            "order": "map order by SM territories when this rank's share is dense and large enough (>= one pose per 16 map cells "
                     "and >= 24 M rays: 1 GPU and 2 GPUs here), the caller's order otherwise"}
+    views = counter_views(c, "config3", 1, ms)
+    if views:
+        res["counters"] = views
     if c.dist_on:
         peer = PeerGather(c.local_rank, per * A)
         sp = int(torch.cuda.current_stream(c.local_rank).cuda_stream)
@@ -924,6 +957,9 @@ def config5(c):
            "frac_hbm": alg / c.world / (ms * 1e-3) / 1e9 / c.hbm_peak, "ingest_ms": omap.ingest_ms,
            "bound": "the one HBM-side case: the field is twice the L2, misses are 32-byte sector gathers from HBM (3.3 TB/s of "
                     "them in caller order, profiles/r02_cfg35_metrics.csv; map order + SM territories turn most into L1 / L2 hits)"}
+    views = counter_views(c, "config5_share", n_total / 2.0e6, ms)   # counters were taken on a 2 M-pose piece
+    if views:
+        res["counters"] = views
     if c.dist_on:
         peer = PeerGather(c.local_rank, chunk * R, nbuf=2)
 

@@ -1,2 +1,8 @@
 mkdir -p gpurun_out
-timeout 600 python tools/r02_gate_probe.py 2>/dev/null | grep gate | tee gpurun_out/r2t_gate.jsonl
+timeout 900 python bench.py > gpurun_out/r2v_bench_n1.json 2> gpurun_out/r2v_bench_n1.err
+tail -c 200 gpurun_out/r2v_bench_n1.err
+python -c "
+import json
+d=json.loads(open('gpurun_out/r2v_bench_n1.json').read().strip().splitlines()[-1])
+print(d['value']/1e9, d['ms_per_step'], d['e2e']['value']/1e9, d['cpu_baseline']['value']/1e9, d['ingest_ms'], 'counters' in d['configs']['config3'])
+"
