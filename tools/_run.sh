@@ -1,8 +1,5 @@
 mkdir -p gpurun_out
-timeout 900 python bench.py > gpurun_out/r2v_bench_n1.json 2> gpurun_out/r2v_bench_n1.err
-tail -c 200 gpurun_out/r2v_bench_n1.err
-python -c "
-import json
-d=json.loads(open('gpurun_out/r2v_bench_n1.json').read().strip().splitlines()[-1])
-print(d['value']/1e9, d['ms_per_step'], d['e2e']['value']/1e9, d['cpu_baseline']['value']/1e9, d['ingest_ms'], 'counters' in d['configs']['config3'])
-"
+(timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_ingest.py tests/test_gpu_fuzz.py -x -q -k "not large_map and not empty_large" 2>&1 | tail -8) > gpurun_out/r2w_memcheck_ingest.log 2>&1
+tail -5 gpurun_out/r2w_memcheck_ingest.log
+(timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_ingest.py -x -q -k "edge_case or synthetic_maps" 2>&1 | tail -8) > gpurun_out/r2w_racecheck_ingest.log 2>&1
+tail -4 gpurun_out/r2w_racecheck_ingest.log
