@@ -50,7 +50,7 @@ march_many_kernel(MarchParams P, const float *__restrict__ ins, float *__restric
         const rl::FirstSample f0 = rl::first_sample(P, g.y, g.x);
         float s, c;
         rl::glibc_sincosf(g.theta, &s, &c);
-        outs[i] = __fmul_rn(rl::march_ray<COUNT, PADDED>(P, g.y, g.x, c, s, steps, f0), P.w.scale);
+        __stcs(outs + i, __fmul_rn(rl::march_ray<COUNT, PADDED>(P, g.y, g.x, c, s, steps, f0), P.w.scale));
     }
     flush_steps<COUNT>(steps, counter);
 }
@@ -147,7 +147,7 @@ march_pose_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_s
         const float r = pose_ray<FAN, COUNT, PADDED>(P, poses + k * pose_stride_floats, angles, j, fov, inc, steps);
         if (OUT == OUT_PEERS) peer_store(peers, i, r);
         else if (OUT == OUT_PEERS4) stage[threadIdx.x] = r;
-        else outs[i] = r;
+        else __stcs(outs + i, r);   // streaming store: the ranges are not read again here (steady state 0.0489 -> 0.0477 ms)
     }
     if (OUT == OUT_PEERS4) {   // peers.offset is a multiple of 4 floats (checked by the host), so is the CTA's base
         __syncthreads();
