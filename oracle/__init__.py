@@ -84,6 +84,7 @@ def lib():
     L.orc_calc_range.restype = C.c_float
     L.orc_calc_range.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float]
     L.orc_calc_range_many.argtypes = [C.c_void_p, f32p, f32p, C.c_int64, C.c_void_p, C.c_int]
+    L.orc_variant_fan.argtypes = [C.c_void_p, f32p, f32p, C.c_int64, C.c_int, C.c_float, C.c_uint, C.c_int]
     L.orc_calc_range_fan.argtypes = [C.c_void_p, f32p, f32p, C.c_int64, C.c_int, C.c_float,
                                      C.c_int64, C.c_void_p, C.c_int]
     L.orc_calc_range_repeat_angles.argtypes = [C.c_void_p, f32p, f32p, f32p, C.c_int64, C.c_int,
@@ -208,6 +209,14 @@ class Marcher:
         lib().orc_calc_range_fan(self._h, poses, outs, b, num_rays, fov, pose_stride_rows, sp,
                                  threads)
         return (outs, s) if steps else outs
+
+    def variant_fan(self, poses, num_rays, fov, mask, threads=1):
+        """NOT the oracle: the fan with a subset of the restatement's fp32 choices flipped
+        (rangelib_oracle.c, section A.7; ``mask`` bits 1 .. 32), for the sensitivity study."""
+        poses = np.ascontiguousarray(poses, dtype=np.float32)
+        outs = np.empty(poses.shape[0] * num_rays, dtype=np.float32)
+        lib().orc_variant_fan(self._h, poses, outs, poses.shape[0], num_rays, fov, int(mask), threads)
+        return outs
 
     def calc_range_repeat_angles(self, ins, angles, outs=None, steps=False, threads=1):
         ins = np.ascontiguousarray(ins, dtype=np.float32)

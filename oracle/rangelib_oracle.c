@@ -513,3 +513,91 @@ ORC_EXPORT void orc_calc_range_repeat_angles(const orc_marcher *m, const float *
     orc_call c = { m, ins, angles, outs, steps, num_angles, 0.0f, 1 };
     orc_parallel_for(num_poses, 64, threads, angles_body, &c);
 }
+
+/* ------------------------------------------------------------------------- */
+/* A.7  convention variants -- NOT the oracle.                               */
+/* The scan half of this file restates range_libc from its published          */
+/* algorithm (PARITY UNPINNED); SURVEY.md A.5 / A.7 list the fp32 details the  */
+/* restatement had to CHOOSE.  This function marches the fork's 4-arg fan with */
+/* any subset of those choices flipped, so that a test can say how far the     */
+/* results would move if upstream had chosen otherwise                        */
+/* (tests/test_convention_sensitivity.py).                                    */
+/*   1  no fused multiply-add anywhere (sample, hit distance, rotation, fan)  */
+/*   2  (p - origin) / scale instead of * (1 / scale)                         */
+/*   4  beam heading accumulated in double, rounded to float once             */
+/*   8  cos / sin evaluated in double, rounded to float                       */
+/*  16  beam heading by repeated fp32 addition (angle += inc)                 */
+/*  32  heading = (-theta - world_angle) - 3 pi / 2 in two fp32 steps         */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+    const orc_marcher *m; const float *ins; float *outs; int num_rays; float fov; unsigned mask;
+} orc_variant_call;
+
+static inline float variant_march(const orc_marcher *m, float x0, float y0, float heading, unsigned mask)
+{
+    float dx, dy;
+    if (mask & 8u) { dx = (float)cos((double)heading); dy = (float)sin((double)heading); }
+    else { dx = cosf(heading); dy = sinf(heading); }
+    const int nofma = (mask & 1u) != 0;
+    const float mr = m->max_range;
+    const float fw = (float)m->width, fh = (float)m->height;
+    float t = 0.0f;
+    while (t < mr) {
+        float fx = nofma ? x0 + dx * t : fmaf(dx, t, x0);
+        float fy = nofma ? y0 + dy * t : fmaf(dy, t, y0);
+        if (!(fx > -1.0f && fx < fw && fy > -1.0f && fy < fh)) return mr;
+        int px = (int)fx, py = (int)fy;
+        float d = m->dist[(size_t)px * m->height + py];
+        if (d <= 0.0f) {
+            float xd = (float)px - x0;
+            float yd = (float)py - y0;
+            return nofma ? sqrtf(xd * xd + yd * yd) : sqrtf(fmaf(xd, xd, yd * yd));
+        }
+        t += fmaxf(d * 0.999f, 1.0f);
+    }
+    return mr;
+}
+
+static void variant_body(void *vc, int64_t b, int64_t e)
+{
+    orc_variant_call *c = (orc_variant_call *)vc;
+    const orc_marcher *m = c->m;
+    const unsigned mask = c->mask;
+    const int n = c->num_rays;
+    const float inc = c->fov / (float)n;
+    const float half = -0.5f * c->fov;
+    const double dinc = (double)c->fov / (double)n, dhalf = -0.5 * (double)c->fov;
+    for (int64_t k = b; k < e; ++k) {
+        const float *p = c->ins + 3 * k;
+        float x, y;
+        if (mask & 2u) { x = (p[0] - m->world_origin_x) / m->world_scale; y = (p[1] - m->world_origin_y) / m->world_scale; }
+        else { x = (p[0] - m->world_origin_x) * m->inv_world_scale; y = (p[1] - m->world_origin_y) * m->inv_world_scale; }
+        float gx, gy;
+        if (mask & 1u) {
+            gx = m->world_cos_angle * x - m->world_sin_angle * y;
+            gy = m->world_sin_angle * x + m->world_cos_angle * y;
+        } else {
+            gx = fmaf(m->world_cos_angle, x, -(m->world_sin_angle * y));
+            gy = fmaf(m->world_sin_angle, x, m->world_cos_angle * y);
+        }
+        float run = p[2] + half;
+        for (int j = 0; j < n; ++j) {
+            float thw;
+            if (mask & 4u) thw = (float)((double)p[2] + (dhalf + (double)j * dinc));
+            else if (mask & 16u) { thw = run; run += inc; }
+            else if (mask & 1u) thw = p[2] + ((float)j * inc + half);
+            else thw = p[2] + fmaf((float)j, inc, half);
+            float thg;
+            if (mask & 32u) thg = (-thw - m->world_angle) - (float)(3.0 * M_PI / 2.0);
+            else thg = -thw + m->rotation_const;
+            c->outs[k * n + j] = variant_march(m, gy, gx, thg, mask) * m->world_scale;
+        }
+    }
+}
+
+ORC_EXPORT void orc_variant_fan(const orc_marcher *m, const float *poses, float *outs, int64_t num_poses,
+                                int num_rays, float fov, unsigned mask, int threads)
+{
+    orc_variant_call c = { m, poses, outs, num_rays, fov, mask };
+    orc_parallel_for(num_poses, 4, threads, variant_body, &c);
+}
