@@ -707,8 +707,8 @@ int32_t launch_pose(rl_marcher *m, const float *d_poses, int64_t stride_rows, co
 // `units` are poses (fan / repeat_angles) or rays (many); every unit has `in_floats` input and
 // `out_floats` output floats.  `launch(first_unit, count, d_in, d_out, stream)` enqueues the kernel.
 template <typename Launch>
-int32_t host_pipeline(rl_marcher *m, const float *ins, int64_t in_stride_floats, int in_floats,
-                      float *outs, int64_t units, int64_t out_floats, Launch launch)
+int32_t host_pipeline_run(rl_marcher *m, const float *ins, int64_t in_stride_floats, int in_floats,
+                          float *outs, int64_t units, int64_t out_floats, Launch launch)
 {
     if (units == 0 || out_floats == 0) return RL_OK;
     int64_t big = (int64_t)(HOST_CHUNK_RAYS / (size_t)out_floats);   // units per staged chunk
@@ -812,6 +812,21 @@ int32_t host_pipeline(rl_marcher *m, const float *ins, int64_t in_stride_floats,
         RL_CUDA(cudaStreamSynchronize(compute));
     }
     return RL_OK;
+}
+
+// A call that fails half way must not leave copies or kernels in flight that still write the caller's buffers or
+// read staging memory the next call may reallocate: drain both streams before reporting the error.
+template <typename Launch>
+int32_t host_pipeline(rl_marcher *m, const float *ins, int64_t in_stride_floats, int in_floats,
+                      float *outs, int64_t units, int64_t out_floats, Launch launch)
+{
+    const int32_t rc = host_pipeline_run(m, ins, in_stride_floats, in_floats, outs, units, out_floats, launch);
+    if (rc != RL_OK) {
+        cudaStreamSynchronize(m->stream);
+        cudaStreamSynchronize(m->stream2);
+        cudaGetLastError();
+    }
+    return rc;
 }
 
 // The persisting-L2 carve-out is a device-wide limit: remember what it was before the first marcher on a
