@@ -131,7 +131,7 @@ march_pose_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_s
                   PeerOut peers)
 {
     release_dependents();
-    __shared__ float stage[OUT == OUT_PEERS4 ? CTA_THREADS : 1];
+    __shared__ __align__(16) float stage[OUT == OUT_PEERS4 ? CTA_THREADS : 1];   // read back as float4
     const int64_t i = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
     uint32_t steps = 0;
     if (i < num_rays_total) {

@@ -29,15 +29,18 @@ __device__ __forceinline__ GridPose world_to_grid(const WorldFrame &w, float xw,
 // INT_MIN does.  Only NaN converts differently (0 here, INT_MIN on x86), hence the one check
 // before the loop: a NaN pose or heading leaves the map at once.
 //
-// Tail mode: 0.4 % of rays need more than TAIL_AFTER steps (they creep along walls at the 1 px
-// minimum step) and, being one dependent load per step, they decide when the kernel ends
-// (profiles/r01_timeline.md).  After TAIL_AFTER plain steps a ray therefore also loads the cell
-// TAIL_AHEAD px further along itself at every step, into a ring of four registers that are only read
-// four steps later, so the touch never stalls the warp and the real sample finds its sector in L1.
-// The touched values never influence the result (the final test on them cannot be true: field values
-// are >= 1); measured 92.3 -> 86.5 us on BASELINE config 2.
-constexpr int TAIL_AFTER = 32;
-constexpr int TAIL_AHEAD = 12;
+// Tail mode: 0.4 % of rays need more than TAIL_AFTER steps (they creep along walls at the 1 px minimum step) and,
+// being one dependent load per step, they decide when the kernel ends (profiles/r01_timeline.md).  After TAIL_AFTER
+// plain steps a ray therefore also touches the cell TAIL_AHEAD px further along itself at every step, so that the
+// real sample finds its sector in L1 a dozen steps later.  The touch never influences a result.
+#ifndef RL_TAIL_AFTER
+#define RL_TAIL_AFTER 32
+#endif
+#ifndef RL_TAIL_AHEAD
+#define RL_TAIL_AHEAD 12
+#endif
+constexpr int TAIL_AFTER = RL_TAIL_AFTER;
+constexpr int TAIL_AHEAD = RL_TAIL_AHEAD;
 
 // The first sample (t = 0) is the pose's own cell whatever the heading, so its load is issued
 // before the heading's sin/cos are evaluated and its latency hides behind that arithmetic.
@@ -95,28 +98,30 @@ __device__ __forceinline__ float march_ray(const MarchParams &P, float x0, float
         if (++it == TAIL_AFTER) { tail = true; break; }
     }
     if (tail) {
-        float j0 = 0.f, j1 = 0.f, j2 = 0.f, j3 = 0.f, keep = 0.f;
+        // The touch is a 4-byte cp.async (LDGSTS through L1) into a shared-memory word nobody reads: it pulls the
+        // sector into L1 like a load does, but has no destination register, so nothing ever waits for it.  (The
+        // first form of this loop touched with ordinary loads into a ring of four registers, read four steps later.
+        // ptxas counts all those loads on ONE scoreboard, and waiting on a scoreboard waits for every load counted on
+        // it -- so each step really waited for the touch issued one step earlier, a full L2 or DRAM latency:
+        // tools/probe_chain.cu, 299 cycles per step across rows against 112 when every sample hits L1.)
+        __shared__ float touch_sink[128];   // a word per thread of the 128-thread march CTAs (never read)
+        const uint32_t sink = (uint32_t)__cvta_generic_to_shared(&touch_sink[threadIdx.x & 127]);
         const float adx = __fmul_rn(dx, (float)TAIL_AHEAD), ady = __fmul_rn(dy, (float)TAIL_AHEAD);
         bool inside = true;
-#define RL_TAIL_STEP(J)                                                                            \
-        {                                                                                          \
-            const float fx = fmaf(dx, t, x0), fy = fmaf(dy, t, y0);                                \
-            px = __float2int_rz(fx);                                                               \
-            py = __float2int_rz(fy);                                                               \
-            if (!PADDED && ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols)) { inside = false; break; } \
-            s = __ldg(P.dist + (px * P.stride + py));                                              \
-            if (COUNT) ++steps;                                                                    \
-            const int ax = __float2int_rz(__fadd_rn(fx, adx)), ay = __float2int_rz(__fadd_rn(fy, ady)); \
-            keep = __fadd_rn(keep, J);                                                             \
-            if (PADDED || ((unsigned)ax < (unsigned)P.rows && (unsigned)ay < (unsigned)P.cols))    \
-                asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(J) : "l"(P.dist + (ax * P.stride + ay))); \
-            t = __fadd_rn(t, s);                                                                   \
-            if (!(t < P.max_range)) break;                                                         \
+        for (;;) {
+            const float fx = fmaf(dx, t, x0), fy = fmaf(dy, t, y0);
+            px = __float2int_rz(fx);
+            py = __float2int_rz(fy);
+            if (!PADDED && ((unsigned)px >= (unsigned)P.rows || (unsigned)py >= (unsigned)P.cols)) { inside = false; break; }
+            s = __ldg(P.dist + (px * P.stride + py));
+            if (COUNT) ++steps;
+            const int ax = __float2int_rz(__fadd_rn(fx, adx)), ay = __float2int_rz(__fadd_rn(fy, ady));
+            if (PADDED || ((unsigned)ax < (unsigned)P.rows && (unsigned)ay < (unsigned)P.cols))
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sink), "l"(P.dist + (ax * P.stride + ay)));
+            t = __fadd_rn(t, s);
+            if (!(t < P.max_range)) break;
         }
-        for (;;) { RL_TAIL_STEP(j0) RL_TAIL_STEP(j1) RL_TAIL_STEP(j2) RL_TAIL_STEP(j3) }
-#undef RL_TAIL_STEP
-        // the touched values (>= 1, +inf or NaN) never influence the result; the test only keeps the loads alive
-        if (__fadd_rn(__fadd_rn(keep, j0), __fadd_rn(j1, __fadd_rn(j2, j3))) < 0.0f) return -1.0f;
+        asm volatile("cp.async.wait_all;" ::: "memory");   // nothing of this thread is in flight when its CTA retires
         if (!inside) return P.max_range;
     }
     if (s == HIT) {

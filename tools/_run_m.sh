@@ -8,5 +8,7 @@ python - <<'PY'
 import json
 j=json.loads(open('gpurun_out/r2m_bench_n1.json').read().strip().splitlines()[-1])
 r=j['roofline']
-print('value', j['value']/1e9, j['ms_per_step'], 'steady', j['steady_state']['value']/1e9, 'e2e', j['e2e']['value']/1e9, 'clocks', j['clocks'])
+print("value", j["value"]/1e9, j["ms_per_step"], "steady", j["steady_state"]["value"]/1e9, "e2e", j["e2e"]["value"]/1e9)
+for k in ("config1","config3","config4","config5"):
+    c=j["configs"][k]; print(k,{x:c[x] for x in c if x in("kernel_ms","rays_per_s","us_per_scan","nominal_rays_per_s","ms")})
 PY
