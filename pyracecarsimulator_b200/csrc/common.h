@@ -63,6 +63,7 @@ struct MarchParams {
     const float *dist;  // the march field (see march_step_of): cell (row, col) is dist[row * stride + col]
     int rows, cols;     // rows = OMap.width (msg.info.height), cols = OMap.height (msg.info.width)
     int stride;         // floats between rows: cols, or cols + 2*pad for the marcher's padded copy
+    uint32_t stride_magic, stride_shift;   // offset / stride == umulhi(offset, magic) >> shift (march.cuh: FastDiv)
     int pad;            // > 0: `pad` cells of NaN surround the map on every side (rows -pad .. rows+pad-1 and
                         // columns -pad .. cols+pad-1 are addressable), and pad exceeds max_range + the tail
                         // look-ahead, so no sample of a ray that starts inside the map needs a bounds test

@@ -50,7 +50,7 @@ march_many_kernel(MarchParams P, const float *__restrict__ ins, float *__restric
         const rl::FirstSample f0 = rl::first_sample(P, g.y, g.x);
         float s, c;
         rl::glibc_sincosf(g.theta, &s, &c);
-        __stcs(outs + i, __fmul_rn(rl::march_ray<COUNT, PADDED>(P, g.y, g.x, c, s, steps, f0), P.w.scale));
+        __stcs(outs + i, __fmul_rn(rl::march_ray<COUNT, PADDED, true>(P, g.y, g.x, c, s, steps, f0), P.w.scale));
     }
     flush_steps<COUNT>(steps, counter);
 }
@@ -108,7 +108,7 @@ __device__ __forceinline__ void peer_store4(const PeerOut &peers, int64_t i, flo
 }
 
 // Beam j of the pose at `p` (x, y, theta in the world frame): the range in metres.
-template <bool FAN, bool COUNT, bool PADDED>
+template <bool FAN, bool COUNT, bool PADDED, bool EARLY>
 __device__ __forceinline__ float pose_ray(const MarchParams &P, const float *__restrict__ p, const float *__restrict__ angles,
                                           int j, float fov, float inc, uint32_t &steps)
 {
@@ -120,7 +120,7 @@ __device__ __forceinline__ float pose_ray(const MarchParams &P, const float *__r
     const rl::FirstSample f0 = rl::first_sample(P, g.y, g.x);
     float s, c;
     rl::glibc_sincosf(thg, &s, &c);
-    return __fmul_rn(rl::march_ray<COUNT, PADDED>(P, g.y, g.x, c, s, steps, f0), P.w.scale);
+    return __fmul_rn(rl::march_ray<COUNT, PADDED, EARLY>(P, g.y, g.x, c, s, steps, f0), P.w.scale);
 }
 
 template <bool FAN, bool COUNT, bool SMALL, int OUT, bool PADDED>
@@ -144,7 +144,7 @@ march_pose_kernel(MarchParams P, const float *__restrict__ poses, int64_t pose_s
         } else {
             k = rl::wide_div(i, num_beams, j);
         }
-        const float r = pose_ray<FAN, COUNT, PADDED>(P, poses + k * pose_stride_floats, angles, j, fov, inc, steps);
+        const float r = pose_ray<FAN, COUNT, PADDED, true>(P, poses + k * pose_stride_floats, angles, j, fov, inc, steps);
         if (OUT == OUT_PEERS) peer_store(peers, i, r);
         else if (OUT == OUT_PEERS4) stage[threadIdx.x] = r;
         else __stcs(outs + i, r);   // streaming store: the ranges are not read again here (steady state 0.0489 -> 0.0477 ms)
@@ -459,7 +459,7 @@ march_territory_kernel(MarchParams P, const float *__restrict__ poses, int64_t p
                     k = rl::wide_div(i, num_beams, j);
                 }
                 if (T.perm) k = __ldg(T.perm + k);   // null: the caller's order by territories (RL_TERRITORY_IDENTITY, measurements)
-                const float rng = pose_ray<FAN, COUNT, PADDED>(P, poses + k * pose_stride_floats, angles, j, fov, inc, steps);
+                const float rng = pose_ray<FAN, COUNT, PADDED, false>(P, poses + k * pose_stride_floats, angles, j, fov, inc, steps);
                 if (PEERS) peer_store(peers, k * num_beams + j, rng);
                 else __stcs(outs + (k * num_beams + j), rng);   // streaming store: the ranges are not read again here
             }
@@ -888,12 +888,15 @@ int32_t rl_marcher_create(const rl_map *map, float max_range_px, uint32_t flags,
     if (!(flags & RL_FLAG_NO_PADDED_FIELD) && max_range_px <= 2048.0f) {
         const int pad = (int)std::ceil(max_range_px) + rl::TAIL_AHEAD + 4;
         const int64_t stride = (int64_t)map->cols + 2 * pad, prow = (int64_t)map->rows + 2 * pad;
-        if (prow * stride < ((int64_t)1 << 31) && cudaMalloc(&m->d_field, (size_t)(prow * stride) * sizeof(float)) == cudaSuccess) {
+        if (prow * stride < ((int64_t)1 << 30) && cudaMalloc(&m->d_field, (size_t)(prow * stride) * sizeof(float)) == cudaSuccess) {
             const int64_t total = prow * stride;
             pad_field_kernel<<<(unsigned)((total + 255) / 256), 256>>>(map->d_step, map->rows, map->cols, pad, m->d_field);
             if (cudaDeviceSynchronize() == cudaSuccess) {
                 m->P.dist = m->d_field + (int64_t)pad * stride + pad;   // cell (0, 0)
                 m->P.stride = (int)stride;
+                const rl::FastDiv sd = make_fast_div((int)stride);
+                m->P.stride_magic = sd.magic;
+                m->P.stride_shift = sd.shift;
                 m->P.pad = pad;
                 m->field_bytes = (size_t)total * sizeof(float);
             } else {

@@ -60,6 +60,91 @@ __device__ __forceinline__ FirstSample first_sample(const MarchParams &P, float 
     return f;
 }
 
+// The look-ahead touch of the tail mode is a 4-byte cp.async (LDGSTS through L1) into a shared-memory word nobody
+// reads: it pulls the sector into L1 like a load does, but has no destination register, so nothing ever waits for
+// it.  (The first form touched with ordinary loads into a ring of four registers, read four steps later.  ptxas
+// counts all those loads on ONE scoreboard, and waiting on a scoreboard waits for every load counted on it -- so
+// each step really waited for the touch issued one step earlier, a full L2 or DRAM latency: tools/probe_chain.cu,
+// 299 cycles per step across rows against 112 when every sample hits L1; tools/sass_ctrl.py shows the barriers.)
+__device__ __forceinline__ uint32_t touch_sink_address()
+{
+    __shared__ float touch_sink[128];   // a word per thread of the 128-thread march CTAs
+    return (uint32_t)__cvta_generic_to_shared(&touch_sink[threadIdx.x & 127]);
+}
+
+__device__ __forceinline__ void touch(uint32_t sink, const float *cell)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sink), "l"(cell));
+}
+
+__device__ __forceinline__ void touches_done()   // nothing of this thread is in flight when its CTA retires
+{
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+// float -> int, toward zero (cvt.rzi saturates), as a volatile asm: the compiler may not sink it below the exit
+// branch of the step it is written in, which is the point of march_padded's ordering.
+__device__ __forceinline__ int trunc_here(float v)
+{
+    int r;
+    asm volatile("cvt.rzi.s32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+
+// The loop over the NaN-padded field (see below), entered with the parameter t of the second sample.  No sample can
+// fall outside the padded field, so the address of the NEXT sample is formed before the exit test of this one is
+// resolved: the 18 cycles from FSETP to the branch run in the shadow of the two float->int conversions instead of
+// ahead of them (tools/probe_chain.cu: cycles per step of a warp that is alone; tools/sass_ctrl.py: the schedule).
+// When the loop ends that address is garbage (t is +inf, NaN or beyond max_range) and is not used.  The cell of the
+// LAST sample, needed for the hit distance, is read off the pointer that sample was loaded through -- keeping the
+// previous t or cell in a register of its own costs one or two MOVs in every step of the unrolled loop, a division
+// of the offset by the row stride (multiply-high) costs half a dozen instructions once per ray.
+template <bool COUNT>
+__device__ __forceinline__ float march_padded(const MarchParams &P, float x0, float y0, float dx, float dy,
+                                              uint32_t &steps, float t)
+{
+    const float HIT = __int_as_float(0x7f800000);
+    float fx = fmaf(dx, t, x0), fy = fmaf(dy, t, y0), s;
+    int idx = __float2int_rz(fx) * P.stride + __float2int_rz(fy);
+    const float *cell;
+    bool tail = true;
+#pragma unroll
+    for (int it = 1; it < TAIL_AFTER; ++it) {
+        cell = P.dist + idx;
+        s = __ldg(cell);
+        if (COUNT) ++steps;
+        t = __fadd_rn(t, s);
+        fx = fmaf(dx, t, x0);
+        fy = fmaf(dy, t, y0);
+        idx = trunc_here(fx) * P.stride + trunc_here(fy);
+        if (!(t < P.max_range)) { tail = false; break; }
+    }
+    if (tail) {
+        const uint32_t sink = touch_sink_address();
+        const float adx = __fmul_rn(dx, (float)TAIL_AHEAD), ady = __fmul_rn(dy, (float)TAIL_AHEAD);
+        for (;;) {
+            cell = P.dist + idx;
+            s = __ldg(cell);
+            if (COUNT) ++steps;
+            touch(sink, P.dist + (__float2int_rz(__fadd_rn(fx, adx)) * P.stride + __float2int_rz(__fadd_rn(fy, ady))));
+            t = __fadd_rn(t, s);
+            fx = fmaf(dx, t, x0);
+            fy = fmaf(dy, t, y0);
+            idx = trunc_here(fx) * P.stride + trunc_here(fy);
+            if (!(t < P.max_range)) break;
+        }
+        touches_done();
+    }
+    if (s == HIT) {   // an occupied cell: inside the map, so its offset from cell (0, 0) is row * stride + column
+        const uint32_t off = ((uint32_t)(uintptr_t)cell - (uint32_t)(uintptr_t)P.dist) >> 2;   // the padded field is below 4 GiB (rl_marcher_create)
+        const uint32_t px = __umulhi(off, P.stride_magic) >> P.stride_shift, py = off - px * (uint32_t)P.stride;
+        const float xd = __fsub_rn((float)(int)px, x0);
+        const float yd = __fsub_rn((float)(int)py, y0);
+        return sqrtf(fmaf(xd, xd, __fmul_rn(yd, yd)));
+    }
+    return P.max_range;
+}
+
 // P.dist is the MARCH FIELD (common.h: march_step_of): s = +inf on an occupied cell, max(0.999 d, 1)
 // elsewhere -- exactly the value the reference's loop adds to t after sampling the cell, computed once
 // per cell by the ingest with the same two fp32 operations.  A hit therefore shows up as t + inf failing
@@ -70,7 +155,11 @@ __device__ __forceinline__ FirstSample first_sample(const MarchParams &P, float 
 // truncation, + TAIL_AHEAD for the look-ahead touch) cells outside it -- inside the padding.  Leaving the
 // map then needs no test of its own: t + NaN = NaN fails `t < max_range` like a hit does, and NaN != +inf
 // sorts it with the misses afterwards.  Three more instructions gone from every step (two ISETP, one BRA).
-template <bool COUNT, bool PADDED>
+// EARLY: the padded loop in its early-address form (march_padded).  It shortens the dependent chain of a step by
+// 17 % and costs about ten instructions more per ray at the exit: the latency-bound plain kernels take it (config 2:
+// single launch 0.0866 -> 0.0824 ms), the issue-bound territory and crash kernels keep the form below (config 5 lost
+// 2-3 % with it).  Same samples, same bits either way.
+template <bool COUNT, bool PADDED, bool EARLY = false>
 __device__ __forceinline__ float march_ray(const MarchParams &P, float x0, float y0, float dx,
                                            float dy, uint32_t &steps, const FirstSample &f0)
 {
@@ -84,6 +173,7 @@ __device__ __forceinline__ float march_ray(const MarchParams &P, float x0, float
     }
     float t = f0.s;   // 0 + step
     if (!(t < P.max_range)) return P.max_range;
+    if (PADDED && EARLY) return march_padded<COUNT>(P, x0, y0, dx, dy, steps, t);
     int px, py, it = 1;
     float s;
     bool tail = false;
@@ -98,14 +188,7 @@ __device__ __forceinline__ float march_ray(const MarchParams &P, float x0, float
         if (++it == TAIL_AFTER) { tail = true; break; }
     }
     if (tail) {
-        // The touch is a 4-byte cp.async (LDGSTS through L1) into a shared-memory word nobody reads: it pulls the
-        // sector into L1 like a load does, but has no destination register, so nothing ever waits for it.  (The
-        // first form of this loop touched with ordinary loads into a ring of four registers, read four steps later.
-        // ptxas counts all those loads on ONE scoreboard, and waiting on a scoreboard waits for every load counted on
-        // it -- so each step really waited for the touch issued one step earlier, a full L2 or DRAM latency:
-        // tools/probe_chain.cu, 299 cycles per step across rows against 112 when every sample hits L1.)
-        __shared__ float touch_sink[128];   // a word per thread of the 128-thread march CTAs (never read)
-        const uint32_t sink = (uint32_t)__cvta_generic_to_shared(&touch_sink[threadIdx.x & 127]);
+        const uint32_t sink = touch_sink_address();
         const float adx = __fmul_rn(dx, (float)TAIL_AHEAD), ady = __fmul_rn(dy, (float)TAIL_AHEAD);
         bool inside = true;
         for (;;) {
@@ -116,12 +199,11 @@ __device__ __forceinline__ float march_ray(const MarchParams &P, float x0, float
             s = __ldg(P.dist + (px * P.stride + py));
             if (COUNT) ++steps;
             const int ax = __float2int_rz(__fadd_rn(fx, adx)), ay = __float2int_rz(__fadd_rn(fy, ady));
-            if (PADDED || ((unsigned)ax < (unsigned)P.rows && (unsigned)ay < (unsigned)P.cols))
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sink), "l"(P.dist + (ax * P.stride + ay)));
+            if (PADDED || ((unsigned)ax < (unsigned)P.rows && (unsigned)ay < (unsigned)P.cols)) touch(sink, P.dist + (ax * P.stride + ay));
             t = __fadd_rn(t, s);
             if (!(t < P.max_range)) break;
         }
-        asm volatile("cp.async.wait_all;" ::: "memory");   // nothing of this thread is in flight when its CTA retires
+        touches_done();
         if (!inside) return P.max_range;
     }
     if (s == HIT) {

@@ -28,7 +28,7 @@ __global__ void chain_kernel(rl::MarchParams P, float x0, float y0, float dx, fl
         uint32_t n = 0;
         const rl::FirstSample f0 = rl::first_sample(P, x0, y0);
         const long long t0 = clock64();
-        const float r = rl::march_ray<true, true>(P, x0, y0, ddx, ddy, n, f0);
+        const float r = rl::march_ray<true, true, true>(P, x0, y0, ddx, ddy, n, f0);
         const long long t1 = clock64();
         if (threadIdx.x == 0) { cycles[pass] = t1 - t0; steps[pass] = n; out[pass] = r; }
     }
@@ -67,6 +67,12 @@ int main()
     P.dist = d + (size_t)pad * stride + pad;
     P.rows = rows; P.cols = cols; P.stride = stride; P.pad = pad;
     P.frows = rows; P.fcols = cols; P.max_range = 300.0f;
+    {   // offset / stride by multiply-high (march.cu: make_fast_div)
+        int sh = 1;
+        while ((1u << sh) < (unsigned)stride) ++sh;
+        P.stride_magic = (uint32_t)((((uint64_t)1 << (31 + sh)) + stride - 1) / stride);
+        P.stride_shift = (uint32_t)(sh - 1);
+    }
     long long *cyc; unsigned *st; float *out;
     CK(cudaMallocManaged(&cyc, 4 * sizeof(long long)));
     CK(cudaMallocManaged(&st, 4 * sizeof(unsigned)));
