@@ -4,7 +4,7 @@
   warm    single launches, L2 left alone
   steady  64 launches back to back on two internal streams (bench.py's `steady_state`)
 and a SHA-1 of the ranges (every variant must give the same bits).
-    python tools/r02_tail_tune.py <lib.so> [<lib.so> ...]      (spawns one child per library)
+    python tools/r02_tail_tune.py <lib.so>[@ENV=VALUE,...] ...      (spawns one child per spec)
 """
 import hashlib
 import json
@@ -85,7 +85,7 @@ def child(lib):
         b.synchronize()
         best = min(best, a.elapsed_time(b) / K)
     rm.set_pipelined("off")
-    print(json.dumps({"probe": "tail_tune", "lib": os.path.basename(lib), "cold_ms_median": round(cold_med, 5),
+    print(json.dumps({"probe": "tail_tune", "lib": os.path.basename(os.environ.get("RL_TUNE_LABEL", lib)), "cold_ms_median": round(cold_med, 5),
                       "cold_ms_min": round(cold_min, 5), "warm_ms_median": round(warm_med, 5), "steady_ms_per_launch": round(best, 5),
                       "cold_grays_per_s": round(P * B / cold_med / 1e6, 2), "steady_grays_per_s": round(P * B / best / 1e6, 2),
                       "sha1": sha.hexdigest()[:12]}), flush=True)
@@ -95,5 +95,11 @@ if __name__ == "__main__":
     if len(sys.argv) >= 3 and sys.argv[1] == "--child":
         child(sys.argv[2])
     else:
-        for lib in sys.argv[1:]:
-            subprocess.run([sys.executable, os.path.abspath(__file__), "--child", lib], check=False)
+        for spec in sys.argv[1:]:   # lib.so[@ENV=VALUE[,ENV=VALUE...]]
+            lib, _, envs = spec.partition("@")
+            env = dict(os.environ)
+            for kv in filter(None, envs.split(",")):
+                k, _, v = kv.partition("=")
+                env[k] = v
+            env["RL_TUNE_LABEL"] = spec
+            subprocess.run([sys.executable, os.path.abspath(__file__), "--child", lib], check=False, env=env)
