@@ -66,6 +66,8 @@ __device__ __forceinline__ FirstSample first_sample(const MarchParams &P, float 
 // counts all those loads on ONE scoreboard, and waiting on a scoreboard waits for every load counted on it -- so
 // each step really waited for the touch issued one step earlier, a full L2 or DRAM latency: tools/probe_chain.cu,
 // 299 cycles per step across rows against 112 when every sample hits L1; tools/sass_ctrl.py shows the barriers.)
+// compute-sanitizer's racecheck reports write-after-write hazards between a thread's successive touches into its
+// own sink word (profiles/r02_sanitizer_racecheck_march.log): the word is write-only, whichever copy lands last.
 __device__ __forceinline__ uint32_t touch_sink_address()
 {
     __shared__ float touch_sink[128];   // a word per thread of the 128-thread march CTAs
