@@ -137,6 +137,7 @@ __device__ __forceinline__ float march_padded(const MarchParams &P, float x0, fl
         }
         touches_done();
     }
+    if (COUNT && s != s) --steps;   // the NaN that ended the ray was read from the padding: the reference reads nothing there
     if (s == HIT) {   // an occupied cell: inside the map, so its offset from cell (0, 0) is row * stride + column
         const uint32_t off = ((uint32_t)(uintptr_t)cell - (uint32_t)(uintptr_t)P.dist) >> 2;   // the padded field is below 4 GiB (rl_marcher_create)
         const uint32_t px = __umulhi(off, P.stride_magic) >> P.stride_shift, py = off - px * (uint32_t)P.stride;
@@ -208,6 +209,7 @@ __device__ __forceinline__ float march_ray(const MarchParams &P, float x0, float
         touches_done();
         if (!inside) return P.max_range;
     }
+    if (COUNT && PADDED && s != s) --steps;   // the NaN that ended the ray was read from the padding: the reference reads nothing there
     if (s == HIT) {
         const float xd = __fsub_rn((float)px, x0);
         const float yd = __fsub_rn((float)py, y0);

@@ -498,3 +498,67 @@ def test_deep_pgm_and_raw_negate(orc, tmp_path):
         omap = range_libc.PyOMap(y, binarise=False)
         occ = orc.omap_from_grid(orc.mapserver_occupancy(img8, negate, 0.65, 0.196, mode), False)
         assert np.array_equal(omap.occupancy(), occ)
+
+
+# --------------------------------------------------------------------------- creeping rays (tail mode)
+def _corridor_map():
+    """A non-square map of corridors two to four cells wide (rays along them creep at the 1 px minimum step for
+    hundreds of steps: the tail mode with its look-ahead touches), with occupied cells in the first / last row and
+    column (hits whose cell offset is 0 or the largest there is) and an open side (rays that leave the map)."""
+    rows, cols = 331, 707
+    occ = np.zeros((rows, cols), np.uint8)
+    occ[0, :] = occ[-1, :] = 1
+    occ[:, 0] = 1                       # the last column stays open except its corners
+    for r in range(6, rows - 6, 9):     # horizontal walls, 1 px thick, every 9 rows, with gaps
+        occ[r, 3:cols - 40] = 1
+        occ[r, 200:204] = 0
+    for c in range(300, cols - 60, 7):  # vertical walls every 7 columns in the lower half
+        occ[170:rows - 4, c] = 1
+    return occ
+
+
+@pytest.mark.parametrize("flags", [0, _native.RL_FLAG_NO_PADDED_FIELD], ids=["padded", "bounds-tested"])
+def test_creeping_rays_through_every_kernel_form(orc, flags):
+    import torch
+    occ = _corridor_map()
+    rows, cols = occ.shape
+    dist = orc.sqrt_dist2(orc.edt_exact(occ))
+    res, origin = 0.05, (-3.0, 1.5, 0.0)
+    omap = range_libc.PyOMap(maps.OccupancyGrid.make(np.where(occ > 0, 100, 0).astype(np.int8).ravel(), cols, rows, res, origin))
+    assert np.array_equal(omap.dist(), dist)
+    rng = np.random.default_rng(8)
+    n = 1500
+    free = np.flatnonzero(dist.ravel() > 0)
+    pick = free[rng.integers(0, free.size, n)]
+    poses = np.empty((n, 3), np.float32)
+    poses[:, 0] = (pick % cols + rng.random(n)) * res + origin[0]
+    poses[:, 1] = (pick // cols + rng.random(n)) * res + origin[1]
+    # headings along the corridors (a few millirad off axis) and a share of arbitrary ones
+    axis = rng.integers(0, 4, n) * (np.pi / 2) + rng.normal(0.0, 4e-3, n)
+    poses[:, 2] = np.where(rng.random(n) < 0.8, axis, rng.uniform(-np.pi, np.pi, n))
+    om = orc.Marcher(dist, 300, res, origin)
+    want, steps = om.calc_range_fan(poses, 33, 0.02, steps=True)
+    assert steps.max() >= 250 and np.mean(steps > 32) > 0.2, "the batch must exercise the tail mode"
+    rm = range_libc.PyRayMarchingGPU(omap, 300, flags=flags)
+    got = np.zeros(n * 33, np.float32)
+    rm.calc_range_fan(poses, got, 0.02, 33)                       # march_pose_kernel<FAN>
+    assert np.array_equal(got, want)
+    angles = np.linspace(-0.01, 0.01, 33, endpoint=False).astype(np.float32)
+    want_a = om.calc_range_repeat_angles(poses, angles)
+    got_a = np.zeros(n * 33, np.float32)
+    rm.calc_range_repeat_angles(poses, angles, got_a)             # march_pose_kernel<!FAN>
+    assert np.array_equal(got_a, want_a)
+    ins = np.repeat(poses, 3, axis=0)
+    ins[:, 2] += np.tile(np.array([0.0, 1e-3, -1e-3], np.float32), n)
+    got_m = np.zeros(ins.shape[0], np.float32)
+    rm.calc_range_many(ins, got_m)                                # march_many_kernel
+    assert np.array_equal(got_m, om.calc_range_many(ins))
+    rm.count_steps(True)                                          # the counting instantiation
+    d_p, d_o = torch.from_numpy(poses).cuda(), torch.zeros(n * 33, dtype=torch.float32, device="cuda")
+    rm.calc_range_fan(d_p, d_o, 0.02, 33)
+    assert rm.last_steps() == int(steps.sum()) and np.array_equal(d_o.cpu().numpy(), want)
+    rm.count_steps(False)
+    sorted_rm = _marcher_with_env(omap, 300, {"RL_SORT_POSES": "1", "RL_SORT_MIN_POSES": "1"}, flags=flags)
+    d_o.zero_()
+    sorted_rm.calc_range_fan(d_p, d_o, 0.02, 33)                  # pose_sort_kernel + march_territory_kernel
+    assert np.array_equal(d_o.cpu().numpy(), want)
