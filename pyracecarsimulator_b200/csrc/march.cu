@@ -687,7 +687,8 @@ int32_t launch_pose(rl_marcher *m, const float *d_poses, int64_t stride_rows, co
     if (peers) {
         // 16-byte stores need this rank's slot to start on a 16-byte boundary; RL_GATHER_VEC=0 forces 4-byte stores
         static const bool vec_ok = [] { const char *e = std::getenv("RL_GATHER_VEC"); return !(e && e[0] == '0'); }();
-        const bool vec = vec_ok && (po.offset % 4) == 0;
+        bool vec = vec_ok && (po.offset % 4) == 0;
+        for (int q = 0; q < (po.multicast ? 1 : po.world); ++q) vec = vec && (reinterpret_cast<uintptr_t>(po.buf[q]) & 15) == 0;
         if (vec) { if (small) RL_LAUNCH(false, true, OUT_PEERS4); else RL_LAUNCH(false, false, OUT_PEERS4); }
         else { if (small) RL_LAUNCH(false, true, OUT_PEERS); else RL_LAUNCH(false, false, OUT_PEERS); }
     } else if (m->count) {
@@ -1189,6 +1190,8 @@ int32_t rl_allgather_ranges(int32_t device, const float *d_src, void *const *pee
     PeerOut po{};
     const int32_t rc = fill_peers(po, peer_bufs, world, rank, slot_rays, flags, "rl_allgather_ranges");
     if (rc != RL_OK) return rc;
+    for (int q = 0; q < (po.multicast ? 1 : world); ++q)
+        if (reinterpret_cast<uintptr_t>(po.buf[q]) & 15) return rl::fail(RL_ERR_BAD_ARG, "rl_allgather_ranges: gathered buffers must be 16-byte aligned");
     const int64_t blocks = ((n + 3) / 4 + 255) / 256;
     if (blocks > 0x7fffffffLL) return rl::fail(RL_ERR_BAD_ARG, "rl_allgather_ranges: too many ranges for one call");
     gather_copy_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_src, n, po);

@@ -25,6 +25,16 @@ def shard_bounds(n: int, world: int, rank: int):
     return lo, hi
 
 
+def gather_set_layout(world: int, slot_rays: int, nbuf: int):
+    """Float offsets of the ``nbuf`` gathered-buffer sets inside one allocation and its total size.  A set holds
+    ``world * slot_rays`` floats; sets start on 256-byte boundaries, because the fused gather stores 16 bytes at a
+    time (``multimem.st.v4`` / ``float4``): with an odd ``slot_rays`` a second set placed right behind the first
+    would start on an 8- or 4-byte boundary only."""
+    used = int(world) * int(slot_rays)
+    stride = -(-used // 64) * 64
+    return [b * stride for b in range(int(nbuf))], max(1, int(nbuf)) * stride
+
+
 class _DevicePtr:
     """Zero-copy torch view of a raw device allocation (``__cuda_array_interface__``)."""
 
@@ -81,7 +91,7 @@ class PeerGather:
         self._next = 0
         self._last = 0
         self.buf_floats = self.world * self.slot_rays
-        n_floats = self.nbuf * self.buf_floats
+        self._set_offsets, n_floats = gather_set_layout(self.world, self.slot_rays, self.nbuf)
         if backend in ("auto", "symm"):
             try:
                 self._init_symm(n_floats, multicast)
@@ -96,8 +106,7 @@ class PeerGather:
             self.backend = "ipc"
         import ctypes as C
         # per buffer set: the `world` base pointers the kernel stores through
-        self._ptr_sets = [(C.c_void_p * self.world)(*[p + b * self.buf_floats * 4 for p in self._base_ptrs])
-                          for b in range(self.nbuf)]
+        self._ptr_sets = [(C.c_void_p * self.world)(*[p + off * 4 for p in self._base_ptrs]) for off in self._set_offsets]
         self.ptrs = self._ptr_sets[0]
 
     def _init_symm(self, n_floats, multicast):
@@ -150,7 +159,7 @@ class PeerGather:
         """This GPU's gathered buffer of the last call (or of set ``buf``): (world * slot_rays,) float32,
         slot r = ranges of rank r."""
         b = self._last if buf is None else int(buf)
-        return self._view[b * self.buf_floats:(b + 1) * self.buf_floats]
+        return self._view[self._set_offsets[b]:self._set_offsets[b] + self.buf_floats]
 
     def _take(self, buf):
         b = self._next if buf is None else int(buf)

@@ -146,3 +146,19 @@ def test_sharded_rollout_matches_single_process(world, n_cars):
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     res = dict(q.get(timeout=5) for _ in range(world))
     assert res == {r: True for r in range(world)}
+
+
+def test_gathered_buffer_sets_start_on_16_byte_boundaries():
+    """The fused gather stores 16 bytes at a time: every buffer set of a PeerGather allocation must start on a
+    16-byte boundary whatever the slot size (an odd slot_rays used to put the second set on a 4- or 8-byte one),
+    and shapes that were already aligned keep their layout."""
+    from pyracecarsimulator_b200.sharded import gather_set_layout
+    for world in (1, 2, 3, 4, 8):
+        for slot in (1, 3, 61, 183, 1080, 4096 * 1080, 125000 * 60, 262144 * 270, 7 * 61 + 1):
+            for nbuf in (1, 2, 3):
+                offs, total = gather_set_layout(world, slot, nbuf)
+                assert len(offs) == nbuf and offs[0] == 0
+                assert all((o * 4) % 256 == 0 for o in offs)
+                assert all(b - a >= world * slot for a, b in zip(offs, offs[1:] + [total]))
+                if (world * slot) % 64 == 0:
+                    assert offs == [b * world * slot for b in range(nbuf)] and total == nbuf * world * slot
